@@ -1,0 +1,165 @@
+"""ctypes binding of ``csrc/libradar_retrieval.so`` (C ABI in ``include/radar_retrieval.h``).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point reports an
+error, a ``RuntimeError`` is raised.  PyTorch is only used for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from typing import Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_PKG_DIR, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libradar_retrieval.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "radar_retrieval.h")
+
+MODE_DPR, MODE_KL, MODE_HYBRID = 0, 1, 2
+PREC_BF16, PREC_FP32 = 0, 1
+ALGO_AUTO, ALGO_SIMT_EXACT, ALGO_TC_FILTER = 0, 1, 2
+NUM_OBS, OBS_PAD, KLPACK, MAX_K = 14, 16, 32, 128
+
+MODE_BY_NAME = {"dpr": MODE_DPR, "kl": MODE_KL, "hybrid": MODE_HYBRID}
+PREC_BY_NAME = {"bf16": PREC_BF16, "fp32": PREC_FP32}
+ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT_EXACT, "tc": ALGO_TC_FILTER}
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+    "-Xcompiler", "-fPIC",
+]
+
+
+class CorpusStruct(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("d", C.c_int32), ("reserved0", C.c_int32),
+        ("emb_f32", C.c_void_p), ("emb_bf16", C.c_void_p), ("logq16", C.c_void_p), ("klpack", C.c_void_p),
+        ("emb_max_norm", C.c_float), ("logq_max_abs", C.c_float), ("idx_offset", C.c_int64),
+    ]
+
+
+class QueriesStruct(C.Structure):
+    _fields_ = [("q", C.c_int64), ("emb_f32", C.c_void_p), ("p16", C.c_void_p), ("entropy", C.c_void_p)]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("precision", C.c_int32), ("algo", C.c_int32), ("k", C.c_int32),
+        ("alpha", C.c_float), ("overfetch", C.c_int32), ("num_sms", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class SearchStats(C.Structure):
+    _fields_ = [
+        ("algo_used", C.c_int32), ("kernel_launches", C.c_int32), ("uncertified", C.c_int64),
+        ("parts", C.c_int32), ("kprime", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "radar_last_error", "radar_abi_version", "radar_device_info", "radar_set_device",
+    "radar_set_profile_events", "radar_pack_embeddings",
+    "radar_kl_prepare_corpus", "radar_kl_prepare_queries", "radar_search_workspace_bytes", "radar_search",
+    "radar_debug_filter_keys", "radar_merge_topk", "radar_rerank_overlap", "radar_gather_bits",
+    "radar_project_normalize",
+]
+
+
+def sources():
+    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh"))]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in sources() + [HEADER_PATH])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a, in tree (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", LIB_PATH, os.path.join(_CSRC, "radar_retrieval.cu"), "-lcudart_static"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the extension (no compute is run).  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU fallback for the retrieval kernels.")
+        l = C.CDLL(LIB_PATH)
+        l.radar_last_error.restype = C.c_char_p
+        l.radar_abi_version.restype = C.c_int
+        l.radar_search_workspace_bytes.restype = C.c_size_t
+        l.radar_search_workspace_bytes.argtypes = [C.POINTER(CorpusStruct), C.c_int64, C.POINTER(SearchParams)]
+        l.radar_search.argtypes = [C.POINTER(CorpusStruct), C.POINTER(QueriesStruct), C.POINTER(SearchParams),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(SearchStats),
+                                   C.c_void_p]
+        l.radar_debug_filter_keys.argtypes = [C.POINTER(CorpusStruct), C.POINTER(QueriesStruct),
+                                              C.POINTER(SearchParams), C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_void_p]
+        l.radar_pack_embeddings.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.radar_kl_prepare_corpus.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]
+        l.radar_kl_prepare_queries.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        l.radar_merge_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]
+        l.radar_rerank_overlap.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+        l.radar_gather_bits.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int64,
+                                        C.c_void_p, C.c_void_p]
+        l.radar_project_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p]
+        l.radar_set_device.argtypes = [C.c_int]
+        l.radar_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
+        l.radar_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        for name in EXPORTS:
+            getattr(l, name)  # raises AttributeError if a declared symbol is not exported
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().radar_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def set_device(device) -> None:
+    import torch
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    check(lib().radar_set_device(idx), "radar_set_device")
+
+
+def device_info():
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    check(lib().radar_device_info(C.byref(a), C.byref(b), C.byref(c)), "radar_device_info")
+    return a.value, b.value, c.value

@@ -1,0 +1,212 @@
+// prep_kernels.cuh -- index-build and query-preparation kernels (HBM-bound, elementwise).
+//   radar_pack_embeddings      replaces faiss.IndexFlatIP.add          (dpr.py:298)
+//   radar_kl_prepare_corpus    K1 corpus side: log tables               (no reference code)
+//   radar_kl_prepare_queries   K1/K3 query side: clamp, mask, entropy   (no reference code)
+//   radar_rerank_overlap       TargetedRetriever.rank_retrieved_passages (rag.py:127-152) on bitmasks
+//   radar_project_normalize    nn.Linear(768,512) + F.normalize         (dpr.py:202-203, :246)
+#pragma once
+#include "common.cuh"
+
+namespace radar {
+
+// one warp per row: fp32 -> bf16 (round to nearest even) and row-norm max-reduction.
+__global__ void __launch_bounds__(256) pack_embeddings_kernel(const float* __restrict__ emb, int64_t n, int d,
+                                                              __nv_bfloat16* __restrict__ out,
+                                                              float* __restrict__ max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    float local_max = 0.0f;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const float4* src = reinterpret_cast<const float4*>(emb + r * d);
+        float ss = 0.0f;
+        for (int c = lane; c < (d >> 2); c += 32) {
+            const float4 v = __ldg(src + c);
+            ss = fmaf(v.x, v.x, ss);
+            ss = fmaf(v.y, v.y, ss);
+            ss = fmaf(v.z, v.z, ss);
+            ss = fmaf(v.w, v.w, ss);
+            if (out) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+                __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 packed;
+                packed.x = *reinterpret_cast<uint32_t*>(&lo);
+                packed.y = *reinterpret_cast<uint32_t*>(&hi);
+                reinterpret_cast<uint2*>(out + r * d)[c] = packed;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        local_max = fmaxf(local_max, sqrtf(ss) * 1.000001f);  // tiny inflation: the norm is only used as a bound
+    }
+    if (lane == 0 && max_norm && local_max > 0.0f)
+        atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(local_max));  // non-negative floats order as ints
+}
+
+__device__ __forceinline__ float canonical_logf(float x) { return static_cast<float>(log(static_cast<double>(x))); }
+
+// one thread per corpus row.
+__global__ void __launch_bounds__(256) kl_prepare_corpus_kernel(const float* __restrict__ probs, int64_t n,
+                                                                int n_obs, float eps, int normalize,
+                                                                float* __restrict__ logq16,
+                                                                __nv_bfloat16* __restrict__ klpack) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float row[kObsPad];
+#pragma unroll
+    for (int j = 0; j < kObsPad; ++j) row[j] = j < n_obs ? probs[r * n_obs + j] : 0.0f;
+    if (normalize) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j)
+            if (j < n_obs) s = __fadd_rn(s, row[j]);
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j)
+            if (j < n_obs) row[j] = __fdiv_rn(row[j], s);
+    }
+    float l[kObsPad];
+#pragma unroll
+    for (int j = 0; j < kObsPad; ++j) {
+        float v = 0.0f;
+        if (j < n_obs) v = canonical_logf(fminf(fmaxf(row[j], eps), 1.0f));
+        l[j] = v;
+    }
+    float4* dst = reinterpret_cast<float4*>(logq16 + r * kObsPad);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    if (klpack) {
+        // [hi(16) | lo(16)] : hi = bf16(L), lo = bf16(L - hi)  (both round-to-nearest)
+        __nv_bfloat16 hi[kObsPad], lo[kObsPad];
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j) {
+            hi[j] = __float2bfloat16_rn(l[j]);
+            lo[j] = __float2bfloat16_rn(__fsub_rn(l[j], __bfloat162float(hi[j])));
+        }
+        uint4* kp = reinterpret_cast<uint4*>(klpack + r * RADAR_KLPACK);
+        const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+        const uint4* l4 = reinterpret_cast<const uint4*>(lo);
+        kp[0] = h4[0];
+        kp[1] = h4[1];
+        kp[2] = l4[0];
+        kp[3] = l4[1];
+    }
+}
+
+// one thread per query.
+__global__ void __launch_bounds__(256) kl_prepare_queries_kernel(const float* __restrict__ probs,
+                                                                 const uint8_t* __restrict__ mask, int64_t q,
+                                                                 int n_obs, float eps, int normalize,
+                                                                 float* __restrict__ p16,
+                                                                 float* __restrict__ entropy) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= q) return;
+    float row[kObsPad];
+#pragma unroll
+    for (int j = 0; j < kObsPad; ++j) row[j] = j < n_obs ? probs[r * n_obs + j] : 0.0f;
+    if (normalize) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j)
+            if (j < n_obs) s = __fadd_rn(s, row[j]);
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j)
+            if (j < n_obs) row[j] = __fdiv_rn(row[j], s);
+    }
+    float h = 0.0f;
+    float pc[kObsPad];
+#pragma unroll
+    for (int j = 0; j < kObsPad; ++j) {
+        float p = 0.0f, lp = 0.0f;
+        if (j < n_obs && (!mask || mask[r * n_obs + j])) {
+            p = fminf(fmaxf(row[j], eps), 1.0f);
+            lp = canonical_logf(p);
+        }
+        pc[j] = p;
+        if (j < n_obs) h = __fmaf_rn(p, lp, h);
+    }
+    float4* dst = reinterpret_cast<float4*>(p16 + r * kObsPad);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = make_float4(pc[4 * j], pc[4 * j + 1], pc[4 * j + 2], pc[4 * j + 3]);
+    entropy[r] = h;
+}
+
+// out[q,k] = table[idx - idx_offset] (0 for padding ids)
+__global__ void __launch_bounds__(256) gather_bits_kernel(const uint16_t* __restrict__ table, int64_t n,
+                                                          const int64_t* __restrict__ idx, int64_t total,
+                                                          int64_t idx_offset, uint16_t* __restrict__ out) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int64_t row = idx[i] - idx_offset;
+    out[i] = (idx[i] >= 0 && row >= 0 && row < n) ? table[row] : uint16_t(0);
+}
+
+// one thread per query: overlap scores in float64 (as Python does) + stable descending order.
+__global__ void __launch_bounds__(128) rerank_overlap_kernel(const uint16_t* __restrict__ case_bits,
+                                                             const uint16_t* __restrict__ missing_bits,
+                                                             int64_t q, int k, double* __restrict__ out_scores,
+                                                             int32_t* __restrict__ out_order) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= q) return;
+    const uint32_t mb = missing_bits[r];
+    const int m = __popc(mb);
+    double* s = out_scores + r * k;
+    int32_t* o = out_order + r * k;
+    for (int j = 0; j < k; ++j) {
+        double sc = 0.5;
+        if (m > 0) {
+            const double overlap = static_cast<double>(__popc(case_bits[r * k + j] & mb));
+            const double cover = overlap / (static_cast<double>(m) + 1e-8);
+            const double div = fmin(overlap / static_cast<double>(m), 1.0) * 0.2;
+            sc = cover + div;
+        }
+        s[j] = sc;
+        o[j] = j;
+    }
+    // stable insertion sort, descending by score (k is small: top_k = 5..32)
+    for (int a = 1; a < k; ++a) {
+        const int32_t oa = o[a];
+        const double sa = s[oa];
+        int b = a - 1;
+        while (b >= 0 && s[o[b]] < sa) {
+            o[b + 1] = o[b];
+            --b;
+        }
+        o[b + 1] = oa;
+    }
+}
+
+// y = normalize(x W^T + b): one CTA per row of x, one thread per output feature group.
+// Arithmetic: fp32 fma chain over the input dim in index order, then sum of squares in feature order
+// via a fixed tree; not a canonical-bit-exact op (torch's GEMM order differs) -- tolerance 1e-5 in tests.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads) project_normalize_kernel(const float* __restrict__ x,
+                                                                     const float* __restrict__ w,
+                                                                     const float* __restrict__ bias, int in_dim,
+                                                                     int out_dim, float* __restrict__ y) {
+    extern __shared__ float sx[];  // in_dim floats + kThreads/32 partials
+    float* partial = sx + in_dim;
+    const int64_t row = blockIdx.x;
+    for (int i = threadIdx.x; i < in_dim; i += kThreads) sx[i] = x[row * in_dim + i];
+    __syncthreads();
+    float ss = 0.0f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // each warp computes output features warp, warp+nwarps, ...: lanes split the input dim (coalesced W reads)
+    constexpr int nwarps = kThreads / 32;
+    for (int o = warp; o < out_dim; o += nwarps) {
+        const float* wr = w + static_cast<int64_t>(o) * in_dim;
+        float acc = 0.0f;
+        for (int i = lane; i < in_dim; i += 32) acc = fmaf(sx[i], __ldg(wr + i), acc);
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (bias) acc += bias[o];
+        if (lane == 0) y[row * out_dim + o] = acc;
+        ss = fmaf(acc, acc, ss);  // identical in every lane
+    }
+    if (lane == 0) partial[warp] = ss;
+    __syncthreads();
+    float tot = 0.0f;
+    for (int i = 0; i < nwarps; ++i) tot += partial[i];
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    __syncthreads();
+    for (int o = threadIdx.x; o < out_dim; o += kThreads) y[row * out_dim + o] *= inv;
+}
+
+}  // namespace radar

@@ -1,0 +1,490 @@
+// radar_retrieval.cu -- C-ABI entry points of libradar_retrieval.so (see include/radar_retrieval.h).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "prep_kernels.cuh"
+#include "scan_kernels.cuh"
+#include "tc_filter.cuh"
+
+namespace radar {
+
+static thread_local char g_err[512] = "";
+// optional CUDA events recorded around the main scan / filter kernel of the next radar_search calls
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct DeviceInfo {
+    int sms = 0, major = 0, minor = 0;
+    bool ok = false;
+};
+
+static int get_device_info(DeviceInfo* out) {
+    static thread_local DeviceInfo cache[64];
+    int dev = 0;
+    RADAR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) {
+        set_error("device ordinal %d out of range", dev);
+        return RADAR_E_CUDA;
+    }
+    if (!cache[dev].ok) {
+        RADAR_CUDA_CHECK(cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+        RADAR_CUDA_CHECK(cudaDeviceGetAttribute(&cache[dev].major, cudaDevAttrComputeCapabilityMajor, dev));
+        RADAR_CUDA_CHECK(cudaDeviceGetAttribute(&cache[dev].minor, cudaDevAttrComputeCapabilityMinor, dev));
+        cache[dev].ok = true;
+    }
+    *out = cache[dev];
+    return RADAR_OK;
+}
+
+// ---- search planning -------------------------------------------------------------------------------
+struct Plan {
+    int algo;
+    int kp;            // candidates a compaction keeps (k on the exact path, k' on the filter path)
+    int R;             // candidates selected per query for re-scoring (= kp)
+    int64_t q_tiles;   // query tiles of the main pass
+    int tile_q;        // rows per query tile (64 scan / 128 filter)
+    int parts;
+    int64_t rows_per_part;
+    // workspace offsets (bytes)
+    size_t off_cand, off_cnt, off_thr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
+    size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
+    int fb_parts;
+    int64_t fb_rows_per_part;
+    size_t total;
+};
+
+static int auto_overfetch(int k) {
+    int kp = ((2 * k + 22) + 15) / 16 * 16;
+    if (kp < 32) kp = 32;
+    if (kp > kCandSoft) kp = kCandSoft;
+    return kp;
+}
+
+static bool tc_supported(const radar_corpus_t* c, int mode, const DeviceInfo& di) {
+    if (di.major != 10) return false;
+    if (mode != RADAR_MODE_KL) {
+        if (!c->emb_bf16 || c->d % 64 != 0 || c->d > 512 || c->d <= 0) return false;
+    }
+    if (mode != RADAR_MODE_DPR && !c->klpack) return false;
+    return c->n >= 1;
+}
+
+static void plan_parts(int64_t q_tiles, int64_t n, int tile_rows, int sms, int waves, int* parts,
+                       int64_t* rows_per_part) {
+    const int64_t c_tiles = ceil_div64(n, tile_rows);
+    int64_t p = 1;
+    if (q_tiles < static_cast<int64_t>(sms) * waves) p = (static_cast<int64_t>(sms) * waves) / q_tiles;
+    if (p > c_tiles) p = c_tiles;
+    if (p < 1) p = 1;
+    if (p > 1024) p = 1024;
+    const int64_t tiles_per_part = ceil_div64(c_tiles, p);
+    p = ceil_div64(c_tiles, tiles_per_part);
+    *parts = static_cast<int>(p);
+    *rows_per_part = tiles_per_part * tile_rows;
+}
+
+static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p, const DeviceInfo& di,
+                     Plan* pl) {
+    memset(pl, 0, sizeof *pl);
+    const int sms = p->num_sms > 0 ? p->num_sms : di.sms;
+    int algo = p->algo;
+    if (algo == RADAR_ALGO_AUTO) algo = tc_supported(c, p->mode, di) ? RADAR_ALGO_TC_FILTER : RADAR_ALGO_SIMT_EXACT;
+    if (algo == RADAR_ALGO_TC_FILTER && !tc_supported(c, p->mode, di)) {
+        set_error("RADAR_ALGO_TC_FILTER needs an sm_100 device, emb_bf16 (d %% 64 == 0, d <= 512) and/or klpack");
+        return di.major != 10 ? RADAR_E_ARCH : RADAR_E_ARG;
+    }
+    pl->algo = algo;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    if (algo == RADAR_ALGO_SIMT_EXACT) {
+        pl->kp = p->k;
+        pl->R = p->k;
+        pl->tile_q = kScanTQ;
+        pl->q_tiles = ceil_div64(q, kScanTQ);
+        plan_parts(pl->q_tiles, c->n, kScanTC, sms, 2, &pl->parts, &pl->rows_per_part);
+    } else {
+        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch(p->k);
+        if (pl->kp < p->k) pl->kp = p->k;
+        if (pl->kp > kCandSoft) pl->kp = kCandSoft;
+        pl->R = pl->kp;
+        pl->tile_q = tc::kBlockM;
+        pl->q_tiles = ceil_div64(q, tc::kBlockM);
+        plan_parts(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), sms, 1, &pl->parts, &pl->rows_per_part);
+    }
+    const int64_t q_pad = pl->q_tiles * pl->tile_q;
+    pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->parts * kCandCap);
+    pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->parts);
+    pl->off_thr = carve(sizeof(float) * q_pad * pl->parts);
+    pl->off_sel = carve(sizeof(uint64_t) * q * pl->R);
+    pl->off_bound = carve(sizeof(float) * q);
+    pl->off_qerr = carve(sizeof(float) * q_pad);
+    pl->off_ucount = carve(sizeof(uint32_t) * 4);
+    pl->off_ulist = carve(sizeof(uint32_t) * q);
+    if (algo == RADAR_ALGO_TC_FILTER) {
+        pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
+        if (p->precision == RADAR_PREC_FP32) {
+            // exact re-run of uncertified queries: sized for up to kFallbackMaxQ queries per pass
+            const int64_t fq = q < tc::kFallbackMaxQ ? q : tc::kFallbackMaxQ;
+            const int64_t f_tiles = ceil_div64(fq, kScanTQ);
+            plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
+            pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
+            pl->off_fb_cnt = carve(sizeof(uint32_t) * f_tiles * kScanTQ * pl->fb_parts);
+            pl->off_fb_sel = carve(sizeof(uint64_t) * fq * p->k);
+        }
+    }
+    pl->total = off;
+    return RADAR_OK;
+}
+
+static int validate_search(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p) {
+    RADAR_ARG_CHECK(c && p, "null corpus/params");
+    RADAR_ARG_CHECK(p->mode >= RADAR_MODE_DPR && p->mode <= RADAR_MODE_HYBRID, "bad mode %d", p->mode);
+    RADAR_ARG_CHECK(p->precision == RADAR_PREC_BF16 || p->precision == RADAR_PREC_FP32, "bad precision %d",
+                    p->precision);
+    RADAR_ARG_CHECK(p->algo >= RADAR_ALGO_AUTO && p->algo <= RADAR_ALGO_TC_FILTER, "bad algo %d", p->algo);
+    RADAR_ARG_CHECK(q >= 0, "negative query count");
+    RADAR_ARG_CHECK(c->n >= 1 && c->n < 0xFFFFFFFFll, "corpus rows %lld out of range [1, 2^32-1)", (long long)c->n);
+    RADAR_ARG_CHECK(p->k >= 1 && p->k <= RADAR_MAX_K, "k=%d out of range [1,%d]", p->k, RADAR_MAX_K);
+    RADAR_ARG_CHECK(p->k <= c->n, "k=%d exceeds corpus rows %lld (clamp k in the caller as dpr.py:308 does)", p->k,
+                    (long long)c->n);
+    if (p->mode != RADAR_MODE_KL) {
+        RADAR_ARG_CHECK(c->emb_f32, "corpus.emb_f32 is required for DPR/hybrid");
+        RADAR_ARG_CHECK(c->d >= 4 && c->d % 4 == 0, "embedding dim %d must be a positive multiple of 4", c->d);
+    }
+    if (p->mode != RADAR_MODE_DPR) RADAR_ARG_CHECK(c->logq16, "corpus.logq16 is required for KL/hybrid");
+    RADAR_ARG_CHECK(c->idx_offset >= 0 && c->idx_offset + c->n < 0xFFFFFFFFll,
+                    "idx_offset + n must stay below 2^32-1");
+    return RADAR_OK;
+}
+
+static int launch_scan(const ScanArgs& a, int64_t q_tiles, cudaStream_t st) {
+    dim3 grid(static_cast<unsigned>(q_tiles), static_cast<unsigned>(a.parts));
+    if (a.mode == RADAR_MODE_DPR) simt_scan_kernel<true, false><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
+    else if (a.mode == RADAR_MODE_KL) simt_scan_kernel<false, true><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
+    else simt_scan_kernel<true, true><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+}  // namespace radar
+
+using namespace radar;
+
+extern "C" {
+
+const char* radar_last_error(void) { return g_err; }
+int radar_abi_version(void) { return RADAR_ABI_VERSION; }
+
+int radar_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    if (sm_count) *sm_count = di.sms;
+    if (cc_major) *cc_major = di.major;
+    if (cc_minor) *cc_minor = di.minor;
+    return RADAR_OK;
+}
+
+int radar_set_device(int device) {
+    RADAR_CUDA_CHECK(cudaSetDevice(device));
+    return RADAR_OK;
+}
+
+int radar_set_profile_events(void* ev_start, void* ev_stop) {
+    g_prof_start = static_cast<cudaEvent_t>(ev_start);
+    g_prof_stop = static_cast<cudaEvent_t>(ev_stop);
+    return RADAR_OK;
+}
+
+int radar_pack_embeddings(const float* emb_f32, int64_t n, int d, uint16_t* emb_bf16, float* max_norm,
+                          void* stream) {
+    RADAR_ARG_CHECK(emb_f32 && n >= 0 && d >= 4 && d % 4 == 0, "pack_embeddings: need emb, n >= 0, d %% 4 == 0");
+    if (n == 0) return RADAR_OK;
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    const int64_t warps_needed = n;
+    int64_t blocks = ceil_div64(warps_needed, 8);
+    const int64_t cap = static_cast<int64_t>(di.sms) * 16;
+    if (blocks > cap) blocks = cap;
+    pack_embeddings_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        emb_f32, n, d, reinterpret_cast<__nv_bfloat16*>(emb_bf16), max_norm);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_kl_prepare_corpus(const float* probs, int64_t n, int n_obs, float eps, int normalize, float* logq16,
+                            uint16_t* klpack, void* stream) {
+    RADAR_ARG_CHECK(probs && logq16 && n >= 0, "kl_prepare_corpus: null pointer");
+    RADAR_ARG_CHECK(n_obs >= 1 && n_obs <= RADAR_NUM_OBS, "n_obs=%d out of range [1,%d]", n_obs, RADAR_NUM_OBS);
+    RADAR_ARG_CHECK(eps > 0.0f && eps < 1.0f, "eps must be in (0,1)");
+    if (n == 0) return RADAR_OK;
+    kl_prepare_corpus_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        probs, n, n_obs, eps, normalize, logq16, reinterpret_cast<__nv_bfloat16*>(klpack));
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_kl_prepare_queries(const float* probs, const uint8_t* mask, int64_t q, int n_obs, float eps,
+                             int normalize, float* p16, float* entropy, void* stream) {
+    RADAR_ARG_CHECK(probs && p16 && entropy && q >= 0, "kl_prepare_queries: null pointer");
+    RADAR_ARG_CHECK(n_obs >= 1 && n_obs <= RADAR_NUM_OBS, "n_obs=%d out of range [1,%d]", n_obs, RADAR_NUM_OBS);
+    RADAR_ARG_CHECK(eps > 0.0f && eps < 1.0f, "eps must be in (0,1)");
+    if (q == 0) return RADAR_OK;
+    kl_prepare_queries_kernel<<<static_cast<unsigned>(ceil_div64(q, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        probs, mask, q, n_obs, eps, normalize, p16, entropy);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+size_t radar_search_workspace_bytes(const radar_corpus_t* corpus, int64_t q, const radar_search_params_t* params) {
+    if (validate_search(corpus, q, params)) return 0;
+    DeviceInfo di;
+    if (get_device_info(&di)) return 0;
+    Plan pl;
+    if (make_plan(corpus, q, params, di, &pl)) return 0;
+    return pl.total + 256;
+}
+
+int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, const radar_search_params_t* params,
+                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                 radar_search_stats_t* stats, void* stream) {
+    RADAR_ARG_CHECK(queries, "null queries");
+    const int64_t q = queries->q;
+    int rc = validate_search(corpus, q, params);
+    if (rc) return rc;
+    RADAR_ARG_CHECK(out_scores && out_idx, "null output pointer");
+    if (params->mode != RADAR_MODE_KL) RADAR_ARG_CHECK(queries->emb_f32, "queries.emb_f32 is required for DPR/hybrid");
+    if (params->mode != RADAR_MODE_DPR)
+        RADAR_ARG_CHECK(queries->p16 && queries->entropy, "queries.p16/entropy are required for KL/hybrid");
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (q == 0) return RADAR_OK;
+    DeviceInfo di;
+    rc = get_device_info(&di);
+    if (rc) return rc;
+    Plan pl;
+    rc = make_plan(corpus, q, params, di, &pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.total) {
+        set_error("workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+        return RADAR_E_WORKSPACE;
+    }
+    RADAR_ARG_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "workspace must be 256-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint64_t* cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+    float* thr = reinterpret_cast<float*>(ws + pl.off_thr);
+    uint64_t* sel = reinterpret_cast<uint64_t*>(ws + pl.off_sel);
+    float* bound = reinterpret_cast<float*>(ws + pl.off_bound);
+    float* qerr = reinterpret_cast<float*>(ws + pl.off_qerr);
+    uint32_t* ucount = reinterpret_cast<uint32_t*>(ws + pl.off_ucount);
+    uint32_t* ulist = reinterpret_cast<uint32_t*>(ws + pl.off_ulist);
+    const float alpha = params->alpha;
+    const float oma = 1.0f - alpha;
+    int launches = 0;
+    int64_t uncertified = 0;
+
+    if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
+        ScanArgs a{};
+        a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
+        a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = nullptr;
+        a.nq = q; a.n = corpus->n; a.d = corpus->d; a.mode = params->mode; a.alpha = alpha; a.oma = oma;
+        a.parts = pl.parts; a.rows_per_part = pl.rows_per_part; a.kp = pl.kp; a.cand = cand; a.cnt = cnt;
+        if (g_prof_start) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
+        rc = launch_scan(a, pl.q_tiles, st);
+        if (rc) return rc;
+        if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
+        ++launches;
+        select_kernel<<<static_cast<unsigned>(q), kSelThreads, 0, st>>>(cand, cnt, nullptr, pl.parts, kCandCap, pl.R,
+                                                                       sel, nullptr);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+        FinalArgs f{};
+        f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 0; f.qmap = nullptr;
+        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx;
+        final_kernel<<<static_cast<unsigned>(q), kFinalThreads, 0, st>>>(f);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+    } else {
+        const bool certify = params->precision == RADAR_PREC_FP32;
+        RADAR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(uint32_t) * 4, st));
+        tc::FilterLaunch fl{};
+        fl.corpus = corpus; fl.queries = queries; fl.mode = params->mode; fl.alpha = alpha; fl.oma = oma;
+        fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part; fl.kp = pl.kp;
+        fl.cand = cand; fl.cnt = cnt; fl.thr = thr; fl.qerr = qerr;
+        fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
+        fl.num_sms = params->num_sms > 0 ? params->num_sms : di.sms;
+        fl.dbg_scores = nullptr;
+        fl.ev_start = g_prof_start; fl.ev_stop = g_prof_stop;
+        int nl = 0;
+        rc = tc::launch_filter(fl, st, &nl);
+        if (rc) return rc;
+        launches += nl;
+        select_kernel<<<static_cast<unsigned>(q), kSelThreads, 0, st>>>(cand, cnt, thr, pl.parts, kCandCap, pl.R, sel,
+                                                                       bound);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+        RescoreArgs r{};
+        r.q_emb = queries->emb_f32; r.p16 = queries->p16; r.entropy = queries->entropy;
+        r.c_emb = corpus->emb_f32; r.logq16 = corpus->logq16; r.qmap = nullptr; r.nq = q; r.d = corpus->d;
+        r.mode = params->mode; r.alpha = alpha; r.oma = oma; r.R = pl.R; r.sel = sel;
+        rescore_kernel<<<static_cast<unsigned>(ceil_div64(q * pl.R, 256)), 256, 0, st>>>(r);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+        FinalArgs f{};
+        f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 1; f.qmap = nullptr;
+        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx;
+        if (certify) {
+            f.bound = bound; f.qerr = qerr; f.uncert_count = ucount; f.uncert_list = ulist;
+        }
+        final_kernel<<<static_cast<unsigned>(q), kFinalThreads, 0, st>>>(f);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        ++launches;
+        if (certify) {
+            // the only host round trip of a search call: 4 bytes, the number of queries to re-run exactly
+            uint32_t h_count = 0;
+            RADAR_CUDA_CHECK(cudaMemcpyAsync(&h_count, ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
+            uncertified = h_count;
+            uint64_t* fb_cand = reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand);
+            uint32_t* fb_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt);
+            uint64_t* fb_sel = reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel);
+            for (int64_t done = 0; done < static_cast<int64_t>(h_count); done += tc::kFallbackMaxQ) {
+                const int64_t nb = (static_cast<int64_t>(h_count) - done) < tc::kFallbackMaxQ
+                                       ? (static_cast<int64_t>(h_count) - done)
+                                       : tc::kFallbackMaxQ;
+                ScanArgs a{};
+                a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
+                a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist + done;
+                a.nq = nb; a.n = corpus->n; a.d = corpus->d; a.mode = params->mode; a.alpha = alpha; a.oma = oma;
+                a.parts = pl.fb_parts; a.rows_per_part = pl.fb_rows_per_part; a.kp = params->k;
+                a.cand = fb_cand; a.cnt = fb_cnt;
+                rc = launch_scan(a, ceil_div64(nb, kScanTQ), st);
+                if (rc) return rc;
+                select_kernel<<<static_cast<unsigned>(nb), kSelThreads, 0, st>>>(fb_cand, fb_cnt, nullptr, pl.fb_parts,
+                                                                                kCandCap, params->k, fb_sel, nullptr);
+                RADAR_CUDA_CHECK(cudaGetLastError());
+                FinalArgs g{};
+                g.sel = fb_sel; g.R = params->k; g.k = params->k; g.mode = params->mode; g.sort = 0;
+                g.qmap = ulist + done; g.idx_offset = corpus->idx_offset; g.out_scores = out_scores;
+                g.out_idx = out_idx;
+                final_kernel<<<static_cast<unsigned>(nb), kFinalThreads, 0, st>>>(g);
+                RADAR_CUDA_CHECK(cudaGetLastError());
+                launches += 3;
+            }
+        }
+    }
+    if (stats) {
+        RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
+        stats->algo_used = pl.algo;
+        stats->kernel_launches = launches;
+        stats->uncertified = uncertified;
+        stats->parts = pl.parts;
+        stats->kprime = pl.kp;
+    }
+    return RADAR_OK;
+}
+
+int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t* queries,
+                            const radar_search_params_t* params, float* out_keys, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    RADAR_ARG_CHECK(queries && out_keys, "debug_filter_keys: null pointer");
+    const int64_t q = queries->q;
+    int rc = validate_search(corpus, q, params);
+    if (rc) return rc;
+    DeviceInfo di;
+    rc = get_device_info(&di);
+    if (rc) return rc;
+    radar_search_params_t p2 = *params;
+    p2.algo = RADAR_ALGO_TC_FILTER;
+    Plan pl;
+    rc = make_plan(corpus, q, &p2, di, &pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.total) {
+        set_error("workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
+        return RADAR_E_WORKSPACE;
+    }
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    tc::FilterLaunch fl{};
+    fl.corpus = corpus; fl.queries = queries; fl.mode = p2.mode; fl.alpha = p2.alpha; fl.oma = 1.0f - p2.alpha;
+    fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part; fl.kp = pl.kp;
+    fl.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
+    fl.cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+    fl.thr = reinterpret_cast<float*>(ws + pl.off_thr);
+    fl.qerr = reinterpret_cast<float*>(ws + pl.off_qerr);
+    fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
+    fl.num_sms = p2.num_sms > 0 ? p2.num_sms : di.sms;
+    fl.dbg_scores = out_keys;
+    int nl = 0;
+    return tc::launch_filter(fl, static_cast<cudaStream_t>(stream), &nl);
+}
+
+int radar_merge_topk(const float* cand_scores, const int64_t* cand_idx, int64_t q, int parts, int k_in, int k_out,
+                     int ascending, float* out_scores, int64_t* out_idx, void* stream) {
+    RADAR_ARG_CHECK(cand_scores && cand_idx && out_scores && out_idx, "merge_topk: null pointer");
+    RADAR_ARG_CHECK(q >= 0 && parts >= 1 && k_in >= 1 && k_out >= 1, "merge_topk: bad sizes");
+    RADAR_ARG_CHECK(static_cast<int64_t>(parts) * k_in <= kMergeCap, "merge_topk: parts*k_in=%lld exceeds %d",
+                    (long long)parts * k_in, kMergeCap);
+    RADAR_ARG_CHECK(k_out <= parts * k_in, "merge_topk: k_out exceeds the candidate count");
+    if (q == 0) return RADAR_OK;
+    merge_kernel<<<static_cast<unsigned>(q), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        cand_scores, cand_idx, q, parts, k_in, k_out, ascending, out_scores, out_idx);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_rerank_overlap(const uint16_t* case_bits, const uint16_t* missing_bits, int64_t q, int k,
+                         double* out_scores, int32_t* out_order, void* stream) {
+    RADAR_ARG_CHECK(case_bits && missing_bits && out_scores && out_order, "rerank_overlap: null pointer");
+    RADAR_ARG_CHECK(q >= 0 && k >= 1 && k <= 1024, "rerank_overlap: bad sizes");
+    if (q == 0) return RADAR_OK;
+    rerank_overlap_kernel<<<static_cast<unsigned>(ceil_div64(q, 128)), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        case_bits, missing_bits, q, k, out_scores, out_order);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_gather_bits(const uint16_t* table, int64_t n, const int64_t* idx, int64_t q, int k, int64_t idx_offset,
+                      uint16_t* out, void* stream) {
+    RADAR_ARG_CHECK(table && idx && out && n >= 0 && q >= 0 && k >= 1, "gather_bits: bad arguments");
+    const int64_t total = q * k;
+    if (total == 0) return RADAR_OK;
+    gather_bits_kernel<<<static_cast<unsigned>(ceil_div64(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        table, n, idx, total, idx_offset, out);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_project_normalize(const float* x, const float* w, const float* bias, int64_t b, int in_dim, int out_dim,
+                            float* y, void* stream) {
+    RADAR_ARG_CHECK(x && w && y && b >= 0 && in_dim >= 1 && out_dim >= 1, "project_normalize: bad arguments");
+    RADAR_ARG_CHECK(in_dim <= 8192, "project_normalize: in_dim too large");
+    if (b == 0) return RADAR_OK;
+    constexpr int kT = 256;
+    const size_t smem = sizeof(float) * (in_dim + kT / 32);
+    project_normalize_kernel<kT><<<static_cast<unsigned>(b), kT, smem, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, in_dim, out_dim, y);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+}  // extern "C"

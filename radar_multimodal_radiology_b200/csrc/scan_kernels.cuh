@@ -1,0 +1,415 @@
+// scan_kernels.cuh -- the exact CUDA-core scan (canonical fp32 arithmetic) and the candidate
+// post-processing kernels shared with the tensor-core filter.
+//
+// Pipeline of one search call (Q x N scores are never written to HBM):
+//   scan / filter kernel : per (query tile, corpus slab) keeps a thresholded candidate buffer
+//                          cand[query][slab][C] of 64-bit composites, compacted to the best k' whenever
+//                          it passes C_SOFT entries (threshold <- k'-th best key)
+//   select_kernel        : per query, best R composites over all slabs (+ bound on everything dropped)
+//   rescore_kernel       : (filter path only) canonical fp32 key of each selected candidate
+//   final_kernel         : per query sort by canonical key, write top-k (+ certificate on the filter path)
+#pragma once
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace radar {
+
+constexpr int kCandCap = 256;   // capacity C of one (query, slab) candidate buffer
+constexpr int kCandSoft = 192;  // compaction trigger; C - C_SOFT >= rows a tile can append per query
+
+constexpr int kScanTQ = 64;  // queries per CTA tile
+constexpr int kScanTC = 64;  // corpus rows per tile
+constexpr int kScanKC = 32;  // embedding columns staged per step
+constexpr int kScanThreads = 256;
+constexpr int kScanLd = kScanTQ + 4;
+
+struct ScanArgs {
+    const float* q_emb;
+    const float* p16;
+    const float* entropy;
+    const float* c_emb;
+    const float* logq16;
+    const uint32_t* qmap;  // nullable: tile row -> query id (exact re-run of uncertified queries)
+    int64_t nq;            // tile rows in use
+    int64_t n;             // corpus rows
+    int d;
+    int mode;
+    float alpha, oma;
+    int parts;
+    int64_t rows_per_part;  // multiple of kScanTC
+    int kp;                 // entries kept by a compaction (= k on this exact path)
+    uint64_t* cand;         // [nq][parts][kCandCap]
+    uint32_t* cnt;          // [nq][parts]
+};
+
+constexpr size_t kScanSmemBytes =
+    sizeof(float) * (2 * kScanKC * kScanLd + 2 * kObsPad * kScanTQ + 2 * kScanTQ) + sizeof(uint32_t) * 2 * kScanTQ +
+    sizeof(uint64_t) * (kScanThreads / 32) * kCandCap;
+
+// warp-cooperative compaction of one candidate buffer: keep the best kp, return the kp-th key.
+__device__ __forceinline__ float warp_compact(uint64_t* __restrict__ buf, int n, int kp, uint64_t* scratch,
+                                              int lane) {
+#pragma unroll
+    for (int e = 0; e < kCandCap / 32; ++e) {
+        const int i = lane + 32 * e;
+        scratch[i] = i < n ? buf[i] : 0ull;
+    }
+    bitonic_sort_desc(scratch, kCandCap, lane, 32, [] { __syncwarp(); });
+    for (int i = lane; i < kp; i += 32) buf[i] = scratch[i];
+    const float t = composite_key(scratch[kp - 1]);
+    __syncwarp();
+    return t;
+}
+
+template <bool HAS_IP, bool HAS_KL>
+__global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* As = reinterpret_cast<float*>(smem_raw);  // [KC][LD]  query chunk, k-major
+    float* Bs = As + kScanKC * kScanLd;              // [KC][LD]  corpus chunk, k-major
+    float* Ps = Bs + kScanKC * kScanLd;              // [16][TQ]
+    float* Ls = Ps + kObsPad * kScanTQ;              // [16][TC]
+    float* Hs = Ls + kObsPad * kScanTC;              // [TQ]
+    float* thr = Hs + kScanTQ;                       // [TQ]
+    uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr + kScanTQ);  // [TQ]
+    uint32_t* qid_s = cnt_s + kScanTQ;                             // [TQ]
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(qid_s + kScanTQ);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int ty = tid >> 4, tx = tid & 15;
+    const int part = blockIdx.y;
+    const int64_t q0 = static_cast<int64_t>(blockIdx.x) * kScanTQ;
+    const int64_t part_begin = static_cast<int64_t>(part) * a.rows_per_part;
+    const int64_t part_end = min(a.n, part_begin + a.rows_per_part);
+
+    if (tid < kScanTQ) {
+        const int64_t qi = q0 + tid;
+        const bool valid = qi < a.nq;
+        const uint32_t qid = valid ? (a.qmap ? a.qmap[qi] : static_cast<uint32_t>(qi)) : 0xFFFFFFFFu;
+        qid_s[tid] = qid;
+        thr[tid] = -CUDART_INF_F;
+        cnt_s[tid] = 0;
+        Hs[tid] = (valid && HAS_KL) ? a.entropy[qid] : 0.0f;
+#pragma unroll
+        for (int j = 0; j < kObsPad; ++j)
+            Ps[j * kScanTQ + tid] = (valid && HAS_KL) ? a.p16[static_cast<int64_t>(qid) * kObsPad + j] : 0.0f;
+    }
+    __syncthreads();
+
+    const int ld_r = tid >> 2;         // tile row this thread stages (0..63)
+    const int ld_k = (tid & 3) * 8;    // first of the 8 columns it stages
+    const uint32_t ld_qid = qid_s[ld_r];
+
+    for (int64_t row0 = part_begin; row0 < part_end; row0 += kScanTC) {
+        float ip[4][4], x[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                ip[i][j] = 0.0f;
+                x[i][j] = 0.0f;
+            }
+        if (HAS_KL) {
+            const int64_t row = row0 + ld_r;
+            const int jq = (tid & 3) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < a.n) v = __ldg(reinterpret_cast<const float4*>(a.logq16 + row * kObsPad + jq));
+            Ls[(jq + 0) * kScanTC + ld_r] = v.x;
+            Ls[(jq + 1) * kScanTC + ld_r] = v.y;
+            Ls[(jq + 2) * kScanTC + ld_r] = v.z;
+            Ls[(jq + 3) * kScanTC + ld_r] = v.w;
+        }
+        if (HAS_IP) {
+            for (int k0 = 0; k0 < a.d; k0 += kScanKC) {
+                const int64_t row = row0 + ld_r;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int kk = ld_k + 4 * h;
+                    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+                    if (k0 + kk < a.d) {
+                        if (ld_qid != 0xFFFFFFFFu)
+                            va = __ldg(reinterpret_cast<const float4*>(a.q_emb + static_cast<int64_t>(ld_qid) * a.d + k0 + kk));
+                        if (row < a.n) vb = __ldg(reinterpret_cast<const float4*>(a.c_emb + row * a.d + k0 + kk));
+                    }
+                    As[(kk + 0) * kScanLd + ld_r] = va.x;
+                    As[(kk + 1) * kScanLd + ld_r] = va.y;
+                    As[(kk + 2) * kScanLd + ld_r] = va.z;
+                    As[(kk + 3) * kScanLd + ld_r] = va.w;
+                    Bs[(kk + 0) * kScanLd + ld_r] = vb.x;
+                    Bs[(kk + 1) * kScanLd + ld_r] = vb.y;
+                    Bs[(kk + 2) * kScanLd + ld_r] = vb.z;
+                    Bs[(kk + 3) * kScanLd + ld_r] = vb.w;
+                }
+                __syncthreads();
+#pragma unroll 8
+                for (int kk = 0; kk < kScanKC; ++kk) {
+                    const float4 av = *reinterpret_cast<const float4*>(As + kk * kScanLd + ty * 4);
+                    const float4 bv = *reinterpret_cast<const float4*>(Bs + kk * kScanLd + tx * 4);
+                    const float aa[4] = {av.x, av.y, av.z, av.w};
+                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ip[i][j] = __fmaf_rn(aa[i], bb[j], ip[i][j]);
+                }
+                __syncthreads();
+            }
+        } else {
+            __syncthreads();
+        }
+        if (HAS_KL) {
+#pragma unroll
+            for (int j = 0; j < kNumObs; ++j) {
+                const float4 pv = *reinterpret_cast<const float4*>(Ps + j * kScanTQ + ty * 4);
+                const float4 lv = *reinterpret_cast<const float4*>(Ls + j * kScanTC + tx * 4);
+                const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+                const float ll[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) x[i][jj] = __fmaf_rn(pp[i], ll[jj], x[i][jj]);
+            }
+        }
+        // threshold filter + append
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ql = ty * 4 + i;
+            if (qid_s[ql] == 0xFFFFFFFFu) continue;
+            const float t = thr[ql];
+            const float h = Hs[ql];
+            uint64_t* buf = a.cand + ((q0 + ql) * a.parts + part) * kCandCap;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t row = row0 + tx * 4 + j;
+                const float key = canonical_key(a.mode, ip[i][j], x[i][j], h, a.alpha, a.oma);
+                if (row < part_end && key >= t) {
+                    const uint32_t slot = atomicAdd(&cnt_s[ql], 1u);
+                    buf[slot] = make_composite(key, static_cast<uint32_t>(row));
+                }
+            }
+        }
+        __syncthreads();
+        for (int ql = warp; ql < kScanTQ; ql += kScanThreads / 32) {
+            const int c = static_cast<int>(cnt_s[ql]);
+            if (c > kCandSoft) {
+                uint64_t* buf = a.cand + ((q0 + ql) * a.parts + part) * kCandCap;
+                const float t = warp_compact(buf, c, a.kp, scratch + warp * kCandCap, lane);
+                if (lane == 0) {
+                    thr[ql] = t;
+                    cnt_s[ql] = a.kp;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid < kScanTQ && q0 + tid < a.nq) a.cnt[(q0 + tid) * a.parts + part] = cnt_s[tid];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// select: per query, the best R composites over all slabs, sorted descending, into sel[qi][R] (0 = empty).
+// bound[qi] = upper bound on the key of every candidate that was ever dropped for this query
+// (-inf when nothing was dropped): max over slabs of the slab's final threshold, and of anything
+// dropped here.  One CTA per query.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 256;
+constexpr int kSelCap = 2048;  // shared-memory working set (composites)
+
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const uint64_t* __restrict__ cand,
+                                                             const uint32_t* __restrict__ cnt,
+                                                             const float* __restrict__ thr_final, int parts,
+                                                             int cap, int R, uint64_t* __restrict__ sel,
+                                                             float* __restrict__ bound) {
+    __shared__ uint64_t s[kSelCap];
+    __shared__ float s_bound;
+    const int64_t qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    auto sync = [] { __syncthreads(); };
+    if (tid == 0) {
+        float b = -CUDART_INF_F;
+        if (thr_final)
+            for (int p = 0; p < parts; ++p) b = fmaxf(b, thr_final[qi * parts + p]);
+        s_bound = b;
+    }
+    __syncthreads();
+
+    int fill = 0;  // uniform across the CTA
+    for (int p = 0; p < parts; ++p) {
+        const int c = static_cast<int>(cnt[qi * parts + p]);
+        const uint64_t* src = cand + (qi * parts + p) * cap;
+        int done = 0;
+        while (done < c) {
+            const int take = min(c - done, kSelCap - fill);
+            for (int i = tid; i < take; i += kSelThreads) s[fill + i] = src[done + i];
+            fill += take;
+            done += take;
+            if (fill == kSelCap) {
+                bitonic_sort_desc(s, kSelCap, tid, kSelThreads, sync);
+                if (tid == 0 && s[R] != 0ull) s_bound = fmaxf(s_bound, composite_key(s[R]));
+                __syncthreads();
+                fill = R;
+            }
+        }
+    }
+    const int P = max(next_pow2(fill), 2);
+    for (int i = fill + tid; i < P; i += kSelThreads) s[i] = 0ull;
+    bitonic_sort_desc(s, P, tid, kSelThreads, sync);
+    if (tid == 0 && fill > R && s[R] != 0ull) s_bound = fmaxf(s_bound, composite_key(s[R]));
+    for (int i = tid; i < R; i += kSelThreads) sel[qi * R + i] = i < fill ? s[i] : 0ull;
+    __syncthreads();
+    if (tid == 0 && bound) bound[qi] = s_bound;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rescore: canonical fp32 key of every selected candidate (one thread per candidate, fma chains in
+// index order -- bit-identical to oracle/radar_oracle.c).
+// ---------------------------------------------------------------------------------------------------
+struct RescoreArgs {
+    const float* q_emb;
+    const float* p16;
+    const float* entropy;
+    const float* c_emb;
+    const float* logq16;
+    const uint32_t* qmap;
+    int64_t nq;
+    int d;
+    int mode;
+    float alpha, oma;
+    int R;
+    uint64_t* sel;
+};
+
+__global__ void __launch_bounds__(256) rescore_kernel(const RescoreArgs a) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= a.nq * a.R) return;
+    const uint64_t c = a.sel[t];
+    if (c == 0ull) return;
+    const int64_t qi = t / a.R;
+    const int64_t qid = a.qmap ? a.qmap[qi] : qi;
+    const uint32_t row = composite_row(c);
+    float ip = 0.0f, x = 0.0f, h = 0.0f;
+    if (a.mode != RADAR_MODE_KL) {
+        const float4* qa = reinterpret_cast<const float4*>(a.q_emb + qid * a.d);
+        const float4* ca = reinterpret_cast<const float4*>(a.c_emb + static_cast<int64_t>(row) * a.d);
+        for (int i = 0; i < (a.d >> 2); ++i) {
+            const float4 u = __ldg(qa + i), v = __ldg(ca + i);
+            ip = __fmaf_rn(u.x, v.x, ip);
+            ip = __fmaf_rn(u.y, v.y, ip);
+            ip = __fmaf_rn(u.z, v.z, ip);
+            ip = __fmaf_rn(u.w, v.w, ip);
+        }
+    }
+    if (a.mode != RADAR_MODE_DPR) {
+        const float* pp = a.p16 + qid * kObsPad;
+        const float* ll = a.logq16 + static_cast<int64_t>(row) * kObsPad;
+#pragma unroll
+        for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(pp[j], __ldg(ll + j), x);
+        h = a.entropy[qid];
+    }
+    a.sel[t] = make_composite(canonical_key(a.mode, ip, x, h, a.alpha, a.oma), row);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// final: sort the R canonical composites of a query, write the top k in API form.
+// Certificate (filter path, FP32 precision): every dropped candidate has filter key <= bound and
+// |canonical - filter| <= qerr, so the result is provably the canonical top-k when
+// bound + qerr < (k-th best canonical key).  Otherwise the query is appended to uncert_list.
+// ---------------------------------------------------------------------------------------------------
+struct FinalArgs {
+    const uint64_t* sel;
+    int R;
+    int k;
+    int mode;
+    int sort;  // 0: sel rows are already in final order
+    const uint32_t* qmap;
+    int64_t idx_offset;
+    float* out_scores;
+    int64_t* out_idx;
+    // certificate (all nullable)
+    const float* bound;
+    const float* qerr;
+    uint32_t* uncert_count;
+    uint32_t* uncert_list;
+};
+
+constexpr int kFinalThreads = 128;
+constexpr int kFinalCap = 512;
+
+__global__ void __launch_bounds__(kFinalThreads) final_kernel(const FinalArgs a) {
+    __shared__ uint64_t s[kFinalCap];
+    const int64_t qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int P = max(next_pow2(a.R), 2);
+    for (int i = tid; i < P; i += kFinalThreads) s[i] = i < a.R ? a.sel[qi * a.R + i] : 0ull;
+    if (a.sort) bitonic_sort_desc(s, P, tid, kFinalThreads, [] { __syncthreads(); });
+    else __syncthreads();
+    const int64_t qid = a.qmap ? a.qmap[qi] : qi;
+    for (int j = tid; j < a.k; j += kFinalThreads) {
+        const uint64_t c = s[j];
+        float sc;
+        int64_t id;
+        if (c != 0ull) {
+            sc = api_score_from_key(a.mode, composite_key(c));
+            id = static_cast<int64_t>(composite_row(c)) + a.idx_offset;
+        } else {
+            sc = a.mode == RADAR_MODE_KL ? CUDART_INF_F : -CUDART_INF_F;
+            id = -1;
+        }
+        a.out_scores[qid * a.k + j] = sc;
+        a.out_idx[qid * a.k + j] = id;
+    }
+    if (a.bound && tid == 0) {
+        const float b = a.bound[qi];
+        bool ok = true;
+        if (b > -CUDART_INF_F) {
+            const uint64_t ck = s[a.k - 1];
+            ok = (ck != 0ull) && (b + a.qerr[qid] < composite_key(ck));
+        }
+        if (!ok) {
+            const uint32_t slot = atomicAdd(a.uncert_count, 1u);
+            a.uncert_list[slot] = static_cast<uint32_t>(qid);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// merge of per-shard top-k lists ([parts][q][k_in], the ncclAllGather layout).  One CTA per query.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMergeCap = 2048;
+
+__global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ scores, const int64_t* __restrict__ idx,
+                                                    int64_t nq, int parts, int k_in, int k_out, int ascending,
+                                                    float* __restrict__ out_scores, int64_t* __restrict__ out_idx) {
+    __shared__ uint64_t s[kMergeCap];
+    const int64_t qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = parts * k_in;
+    const int P = max(next_pow2(total), 2);
+    for (int i = tid; i < P; i += 256) {
+        uint64_t c = 0ull;
+        if (i < total) {
+            const int p = i / k_in, j = i - p * k_in;
+            const int64_t o = (static_cast<int64_t>(p) * nq + qi) * k_in + j;
+            const int64_t id = idx[o];
+            if (id >= 0) {
+                const float sc = scores[o];
+                c = make_composite(ascending ? __fsub_rn(0.0f, sc) : sc, static_cast<uint32_t>(id));
+            }
+        }
+        s[i] = c;
+    }
+    bitonic_sort_desc(s, P, tid, 256, [] { __syncthreads(); });
+    for (int j = tid; j < k_out; j += 256) {
+        const uint64_t c = s[j];
+        if (c != 0ull) {
+            const float key = composite_key(c);
+            out_scores[qi * k_out + j] = ascending ? __fsub_rn(0.0f, key) : key;
+            out_idx[qi * k_out + j] = static_cast<int64_t>(composite_row(c));
+        } else {
+            out_scores[qi * k_out + j] = ascending ? CUDART_INF_F : -CUDART_INF_F;
+            out_idx[qi * k_out + j] = -1;
+        }
+    }
+}
+
+}  // namespace radar

@@ -1,0 +1,612 @@
+// tc_filter.cuh -- tcgen05 (5th-gen tensor core) filter kernel for sm_100a.
+//
+// One CTA per SM, persistent over work items (query tile of 128 rows, corpus slab).
+//   * the QUERY tile is the A operand and lives in TENSOR MEMORY for the whole slab sweep
+//     (bf16 pairs packed in 32-bit TMEM columns, written once per item with tcgen05.st) -- shared
+//     memory holds nothing but the streamed corpus tiles;
+//   * CORPUS tiles are the B operand: TMA (cp.async.bulk.tensor.2d, 128B/64B swizzle) streams
+//     BLOCK_N x 64 bf16 K-blocks of the embedding matrix (and one BLOCK_N x 32 block of the
+//     [log q hi | log q lo] pack) through an mbarrier ring of kStages shared-memory slots;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (A from TMEM, B from smem
+//     descriptors) into one of kAccStages fp32 accumulators in TMEM;
+//   * four epilogue warps read the accumulator back with tcgen05.ld (one query row per thread),
+//     compare against the row's running threshold and append survivors to the row's candidate buffer
+//     in global memory -- the Q x N score matrix never exists outside TMEM.
+//
+// Filter value for (query i, case n):
+//     DPR    f = sum_t bf16(e_q[t]) bf16(e_c[t])
+//     KL     f = sum_j (p_hi+p_lo)[j] (L_hi+L_lo)[n][j]                  (all four hi/lo products)
+//     hybrid f = sum_t bf16(alpha e_q[t]) bf16(e_c[t]) + sum_j (v_hi+v_lo)[j] (L_hi+L_lo)[n][j],  v = (1-alpha) p
+// and the ranking key handed to the candidate buffer is f - shift_i, shift = H (KL) / (1-alpha) H (hybrid),
+// i.e. it approximates the canonical key of common.cuh within qerr_i (see query_pack_kernel).
+#pragma once
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "scan_kernels.cuh"
+
+namespace radar {
+namespace tc {
+
+constexpr int kBlockM = 128;          // query rows per tile == TMEM lanes
+constexpr int kFallbackMaxQ = 4096;   // uncertified queries re-run per exact pass
+constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int kStages = 8;            // shared-memory ring slots
+constexpr int kStageBytes = 16384;    // 128 rows x 128 B
+constexpr int kTmemCols = 512;
+constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
+constexpr int kAKlCols = 16;          // [p_hi (8 cols) | p_lo (8 cols)]
+constexpr uint32_t kSpinLimit = 1u << 27;
+
+__host__ __device__ constexpr int block_n_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? 112 : 128; }
+__host__ __device__ constexpr int acc_stages_for_mode(int mode) { return mode == RADAR_MODE_KL ? 3 : 2; }
+__host__ __device__ constexpr int acc_col0_for_mode(int mode) {
+    return mode == RADAR_MODE_DPR ? kAIpCols : (mode == RADAR_MODE_HYBRID ? kAIpCols + 32 : 128);
+}
+__host__ __device__ constexpr int a_kl_col_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? kAIpCols : 0; }
+// bf16 elements per packed query row
+__host__ __device__ inline int a_cols_for(int mode, int d) {
+    return (mode != RADAR_MODE_KL ? d : 0) + (mode != RADAR_MODE_DPR ? 2 * kObsPad : 0);
+}
+
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * kStageBytes +
+                              4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ + 256 /*barriers*/;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) {
+            printf("radar tc_filter: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T ; kind::f16 with bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
+// shared-memory matrix descriptor, K-major operand, swizzled canonical layout
+//   SW128: rows of 128 B, 8-row atoms 1024 B apart (layout type 2);  SW64: rows of 64 B, atoms 512 B apart (type 4)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // start address,   bits [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                            // LBO (ignored for swizzled K-major), bits [16,30)
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;   // SBO,             bits [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                            // descriptor version 1 (sm_100)
+    d |= static_cast<uint64_t>(layout_type & 7u) << 61;             // swizzle mode,    bits [61,64)
+    return d;
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    // kind::f16: D=F32 (bits 4-5 = 1), A=BF16 (bits 7-9 = 1), B=BF16 (bits 10-12 = 1), K-major A and B,
+    // N>>3 at bits 17-22, M>>4 at bits 24-28
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(kBlockM >> 4) << 24);
+}
+
+// ---- query pack: fp32 queries -> bf16 A rows + per-query shift / error bound -----------------------------
+// apack row layout (bf16): [ d embedding values (scaled by alpha in hybrid) | v_hi (16) | v_lo (16) ]
+// qmeta[row] = {shift, qerr}.  One warp per packed row; rows >= q are zero-filled.
+struct PackArgs {
+    const float* q_emb;
+    const float* p16;
+    const float* entropy;
+    int64_t q, q_pad;
+    int d, mode;
+    float alpha, oma;
+    float emb_max_norm, logq_max_abs;
+    uint16_t* apack;
+    float* qshift;  // [q_pad]
+    float* qerr;    // [q_pad]
+};
+
+__global__ void __launch_bounds__(256) query_pack_kernel(const PackArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= a.q_pad) return;
+    const bool has_ip = a.mode != RADAR_MODE_KL, has_kl = a.mode != RADAR_MODE_DPR;
+    const int cols = a_cols_for(a.mode, a.d);
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(a.apack) + row * cols;
+    const bool valid = row < a.q;
+    float ss = 0.0f, sv = 0.0f;
+    if (has_ip) {
+        const float scale = a.mode == RADAR_MODE_HYBRID ? a.alpha : 1.0f;
+        for (int c = lane; c < a.d; c += 32) {
+            const float v = valid ? __fmul_rn(scale, a.q_emb[row * a.d + c]) : 0.0f;
+            ss = fmaf(v, v, ss);
+            dst[c] = __float2bfloat16_rn(v);
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (has_kl) {
+        const float scale = a.mode == RADAR_MODE_HYBRID ? a.oma : 1.0f;
+        if (lane < kObsPad) {
+            const float v = valid ? __fmul_rn(scale, a.p16[row * kObsPad + lane]) : 0.0f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+            dst[(has_ip ? a.d : 0) + lane] = hi;
+            dst[(has_ip ? a.d : 0) + kObsPad + lane] = lo;
+            sv = fabsf(v);
+        }
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if (lane == 0) {
+        float shift = 0.0f;
+        if (valid && has_kl) shift = a.mode == RADAR_MODE_HYBRID ? __fmul_rn(a.oma, a.entropy[row]) : a.entropy[row];
+        // |canonical key - filter key| <= qerr  (derivation in DESIGN.md, "certificate"):
+        //   bf16 RN of both embedding operands: (2^-8 + 2^-18) |a||c| ; tensor-core fp32 accumulation of <= 576
+        //   exact products and the canonical fp32 chain: <= 2^-13 (|a||c| + sum|v||L|) ; hi/lo split of v and L:
+        //   2^-17 sum|v||L| ; canonical combine / shift roundings: 2^-20 of the magnitudes involved.
+        const float ip_mag = sqrtf(ss) * a.emb_max_norm;
+        const float kl_mag = sv * a.logq_max_abs;
+        const float e = 0.00403f * ip_mag + 1.6e-4f * kl_mag + 1e-6f * (fabsf(shift) + ip_mag + kl_mag) + 1e-30f;
+        a.qshift[row] = shift;
+        a.qerr[row] = e;
+    }
+}
+
+// ---- the filter kernel ------------------------------------------------------------------------------
+struct FilterArgs {
+    const uint16_t* apack;
+    const float* qshift;
+    int64_t q;          // real queries
+    int64_t q_tiles;
+    int64_t n;          // corpus rows
+    int d;
+    int parts;
+    int64_t rows_per_part;  // multiple of BLOCK_N
+    int kp;
+    uint64_t* cand;  // [q_pad][parts][kCandCap]
+    uint32_t* cnt;   // [q_pad][parts]
+    float* thr;      // [q_pad][parts]  final thresholds
+    float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_constant__ CUtensorMap map_kl,
+                 const FilterArgs a) {
+    constexpr bool HAS_IP = MODE != RADAR_MODE_KL;
+    constexpr bool HAS_KL = MODE != RADAR_MODE_DPR;
+    constexpr int BLOCK_N = block_n_for_mode(MODE);
+    constexpr int ACC_STAGES = acc_stages_for_mode(MODE);
+    constexpr int ACC_COL0 = acc_col0_for_mode(MODE);
+    constexpr int A_KL_COL = a_kl_col_for_mode(MODE);
+    constexpr uint32_t IDESC = make_idesc(BLOCK_N);
+    constexpr uint32_t IP_BYTES = BLOCK_N * 128, KL_BYTES = BLOCK_N * 64;
+    static_assert(ACC_COL0 + ACC_STAGES * BLOCK_N <= kTmemCols, "TMEM budget");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* stage_base = smem;
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* bars = scratch + 4 * kCandCap;
+    uint64_t* full_bar = bars;                       // [kStages]
+    uint64_t* empty_bar = bars + kStages;            // [kStages]
+    uint64_t* tfull_bar = bars + 2 * kStages;        // [ACC_STAGES]
+    uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]
+    uint64_t* aready_bar = tempty_bar + ACC_STAGES;  // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = HAS_IP ? a.d / 64 : 0;
+    const int64_t items = a.q_tiles * a.parts;
+
+    if (warp == 0 && lane == 0) {
+        if (HAS_IP) prefetch_tmap(&map_emb);
+        if (HAS_KL) prefetch_tmap(&map_kl);
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);
+        }
+        mbar_init(aready_bar, 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+                const int part = static_cast<int>(item / a.q_tiles);
+                const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+                const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
+                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], IP_BYTES);
+                        tma_load_2d(&map_emb, &full_bar[s], stage_base + s * kStageBytes, kb * 64,
+                                    static_cast<int>(row0));
+                    }
+                    if (HAS_KL) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], KL_BYTES);
+                        tma_load_2d(&map_kl, &full_bar[s], stage_base + s * kStageBytes, 0, static_cast<int>(row0));
+                        ++it;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            uint32_t it = 0, tile = 0, item_no = 0;
+            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
+                const int part = static_cast<int>(item / a.q_tiles);
+                const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+                const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+                mbar_wait(aready_bar, item_no & 1);  // this item's query tile is in TMEM
+                tc_fence_after();
+                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++tile) {
+                    const uint32_t as = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
+                    mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogue drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + ACC_COL0 + as * BLOCK_N;
+                    uint32_t acc = 0;
+                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * kStageBytes), 1024, 2);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 16) per 64-wide block; +32 B per step
+                            umma_ts(d_tmem, tmem_base + kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, acc);
+                            acc = 1;
+                        }
+                        umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+                    }
+                    if (HAS_KL) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * kStageBytes), 512, 4);
+                        const uint32_t a_hi = tmem_base + A_KL_COL, a_lo = a_hi + 8;
+                        umma_ts(d_tmem, a_hi, bdesc, IDESC, acc);      // v_hi . L_hi
+                        umma_ts(d_tmem, a_hi, bdesc + 2, IDESC, 1);    // v_hi . L_lo
+                        umma_ts(d_tmem, a_lo, bdesc, IDESC, 1);        // v_lo . L_hi
+                        umma_ts(d_tmem, a_lo, bdesc + 2, IDESC, 1);    // v_lo . L_lo
+                        umma_commit(&empty_bar[s]);
+                        ++it;
+                    }
+                    umma_commit(&tfull_bar[as]);  // accumulator complete
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps (2..5) ================================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int r_in_tile = quad * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        uint64_t* my_scratch = scratch + (warp - 2) * kCandCap;
+        const int a_cols = a_cols_for(MODE, a.d);  // bf16 per packed row
+        uint32_t tile = 0, item_no = 0;
+        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
+            const int64_t qtile = item % a.q_tiles;
+            const int part = static_cast<int>(item / a.q_tiles);
+            const int64_t qrow = qtile * kBlockM + r_in_tile;
+            const bool valid = qrow < a.q;
+            const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+            const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+            // ---- A tile -> TMEM (every MMA of the previous item has completed: its last accumulator was consumed) ----
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(a.apack + qrow * a_cols);
+                const int ip_chunks = HAS_IP ? a.d / 16 : 0;  // 16 bf16 = 8 TMEM columns per chunk
+                for (int c = 0; c < ip_chunks; ++c) {
+                    const uint4 u0 = __ldg(src + 2 * c), u1 = __ldg(src + 2 * c + 1);
+                    const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    tmem_st_x8(tmem_base + lane_addr + c * 8, v);
+                }
+                if (HAS_KL) {
+                    const uint4* ksrc = src + 2 * ip_chunks;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint4 u0 = __ldg(ksrc + 2 * c), u1 = __ldg(ksrc + 2 * c + 1);
+                        const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                        tmem_st_x8(tmem_base + lane_addr + A_KL_COL + c * 8, v);
+                    }
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(aready_bar);
+            }
+            const float shift = a.qshift[qrow];
+            float thr = -CUDART_INF_F;                                    // in canonical-key units
+            float thr_cmp = valid ? -CUDART_INF_F : CUDART_INF_F;         // in accumulator units
+            int cnt = 0;
+            uint64_t* buf = a.cand + (qrow * a.parts + part) * kCandCap;
+
+            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++tile) {
+                const uint32_t as = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N;
+#pragma unroll
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    constexpr int kFull = 32;
+                    const int width = (BLOCK_N - c) < kFull ? (BLOCK_N - c) : kFull;  // 32 or 16 (compile time after unroll)
+                    float v[32];
+                    if (width == 32) tmem_ld_x32(t_acc + c, v);
+                    else tmem_ld_x16(t_acc + c, v);
+                    tmem_wait_ld();
+                    float m = v[0];
+#pragma unroll
+                    for (int j = 1; j < 32; ++j)
+                        if (j < width) m = fmaxf(m, v[j]);
+                    if (a.dbg_scores && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < width && row0 + c + j < a.n) a.dbg_scores[qrow * a.n + row0 + c + j] = v[j] - shift;
+                    }
+                    const bool hit = m >= thr_cmp;
+                    if (__any_sync(0xffffffffu, hit)) {
+                        if (hit) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                if (j < width && v[j] >= thr_cmp) {
+                                    const int64_t row = row0 + c + j;
+                                    if (row < row_end) buf[cnt++] = make_composite(__fsub_rn(v[j], shift), static_cast<uint32_t>(row));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > kCandSoft);
+                        while (need) {
+                            const int src_lane = __ffs(need) - 1;
+                            need &= need - 1;
+                            uint64_t* b = reinterpret_cast<uint64_t*>(
+                                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src_lane));
+                            const int n_src = __shfl_sync(0xffffffffu, cnt, src_lane);
+                            const float t = warp_compact(b, n_src, a.kp, my_scratch, lane);
+                            if (lane == src_lane) {
+                                thr = t;
+                                thr_cmp = __fadd_rn(t, shift);
+                                cnt = a.kp;
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+            a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
+            a.thr[qrow * a.parts + part] = thr;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        RADAR_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !p) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable");
+            return RADAR_E_CUDA;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    *out = fn;
+    return RADAR_OK;
+}
+
+static int encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint32_t box_inner,
+                          uint32_t box_rows, CUtensorMapSwizzle swz) {
+    EncodeTiledFn fn;
+    int rc = get_encode_fn(&fn);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {inner * sizeof(uint16_t)};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu box=%ux%u)", (int)r,
+                  (unsigned long long)inner, (unsigned long long)rows, box_inner, box_rows);
+        return RADAR_E_CUDA;
+    }
+    return RADAR_OK;
+}
+
+struct FilterLaunch {
+    const radar_corpus_t* corpus;
+    const radar_queries_t* queries;
+    int mode;
+    float alpha, oma;
+    int64_t q, q_tiles;
+    int parts;
+    int64_t rows_per_part;
+    int kp;
+    uint64_t* cand;
+    uint32_t* cnt;
+    float* thr;
+    float* qerr;      // [q_pad]
+    uint16_t* apack;  // [q_pad][a_cols] followed by qshift [q_pad] floats
+    int num_sms;
+    float* dbg_scores;
+    cudaEvent_t ev_start, ev_stop;  // optional: recorded around the filter kernel only
+};
+
+template <int MODE>
+static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cudaStream_t st) {
+    constexpr int BLOCK_N = block_n_for_mode(MODE);
+    CUtensorMap map_emb, map_kl;
+    memset(&map_emb, 0, sizeof map_emb);
+    memset(&map_kl, 0, sizeof map_kl);
+    int rc;
+    if (MODE != RADAR_MODE_KL) {
+        rc = encode_2d_bf16(&map_emb, fl.corpus->emb_bf16, fl.corpus->d, fl.corpus->n, 64, BLOCK_N,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    if (MODE != RADAR_MODE_DPR) {
+        rc = encode_2d_bf16(&map_kl, fl.corpus->klpack, RADAR_KLPACK, fl.corpus->n, RADAR_KLPACK, BLOCK_N,
+                            CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+    }
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[MODE]) {
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kSmemBytes)));
+        attr_set[MODE] = true;
+    }
+    const int64_t items = fl.q_tiles * fl.parts;
+    const int grid = static_cast<int>(items < fl.num_sms ? items : fl.num_sms);
+    if (fl.ev_start) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_start, st));
+    tc_filter_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(map_emb, map_kl, fa);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    if (fl.ev_stop) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_stop, st));
+    return RADAR_OK;
+}
+
+// apack region layout: [q_pad * a_cols] uint16, then (256-byte aligned) qshift [q_pad] floats
+static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
+    size_t b = sizeof(uint16_t) * static_cast<size_t>(q_pad) * a_cols_for(mode, d);
+    b = (b + 255) / 256 * 256;
+    return b + sizeof(float) * static_cast<size_t>(q_pad);
+}
+
+static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches) {
+    const int64_t q_pad = fl.q_tiles * kBlockM;
+    const int cols = a_cols_for(fl.mode, fl.corpus->d);
+    size_t shift_off = (sizeof(uint16_t) * static_cast<size_t>(q_pad) * cols + 255) / 256 * 256;
+    float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fl.apack) + shift_off);
+    PackArgs pa{};
+    pa.q_emb = fl.queries->emb_f32; pa.p16 = fl.queries->p16; pa.entropy = fl.queries->entropy;
+    pa.q = fl.q; pa.q_pad = q_pad; pa.d = fl.corpus->d; pa.mode = fl.mode; pa.alpha = fl.alpha; pa.oma = fl.oma;
+    pa.emb_max_norm = fl.corpus->emb_max_norm; pa.logq_max_abs = fl.corpus->logq_max_abs;
+    pa.apack = fl.apack; pa.qshift = qshift; pa.qerr = fl.qerr;
+    query_pack_kernel<<<static_cast<unsigned>((q_pad * 32 + 255) / 256), 256, 0, st>>>(pa);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    FilterArgs fa{};
+    fa.apack = fl.apack; fa.qshift = qshift; fa.q = fl.q; fa.q_tiles = fl.q_tiles; fa.n = fl.corpus->n;
+    fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
+    fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.dbg_scores = fl.dbg_scores;
+    int rc;
+    if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR>(fl, fa, st);
+    else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL>(fl, fa, st);
+    else rc = launch_filter_mode<RADAR_MODE_HYBRID>(fl, fa, st);
+    if (rc) return rc;
+    *launches = 2;
+    return RADAR_OK;
+}
+
+}  // namespace tc
+}  // namespace radar

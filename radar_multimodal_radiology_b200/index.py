@@ -1,0 +1,346 @@
+"""GPU flat index: the operator that replaces ``faiss.IndexFlatIP`` underneath RADAR's retrieval API.
+
+Reference call sites (annotate_retrieve/modeling_dense_passage_retrieval.py):
+    ``faiss.IndexFlatIP(d)`` :297, ``index.add(float32[N,d])`` :298, ``index.ntotal`` :300,
+    ``index.search(float32[nq,d], k) -> (D float32[nq,k] descending, I int64[nq,k])`` :313,
+    truthiness of the index object :310.
+``RadarIndex`` keeps those four members (``GpuIndexFlatIP`` is the numpy-in / numpy-out spelling a faiss
+user expects) and extends ``search`` with the pieces north_star names: per-query observation
+probabilities (KL), observation masks, and the ``hybrid_alpha`` fusion -- all executed by the sm_100a
+kernels in ``csrc/`` through the C ABI of ``include/radar_retrieval.h``.  PyTorch owns every buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+
+@dataclass
+class SearchStats:
+    algo_used: int = 0
+    kernel_launches: int = 0
+    uncertified: int = 0
+    parts: int = 0
+    kprime: int = 0
+
+
+def _as_device_f32(x: ArrayLike, device: torch.device) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x, dtype=torch.float32)
+    return x.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def prepare_queries(probs: ArrayLike, mask: Optional[ArrayLike], device, eps: float = 1e-8,
+                    normalize: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(p16 float32[Q,16], entropy float32[Q]) on ``device`` -- ``radar_kl_prepare_queries``."""
+    device = torch.device(device)
+    p = _as_device_f32(probs, device)
+    if p.dim() != 2 or p.shape[1] != L.NUM_OBS:
+        raise ValueError(f"query_probs must be [Q,{L.NUM_OBS}], got {tuple(p.shape)}")
+    m = None
+    if mask is not None:
+        if isinstance(mask, np.ndarray):
+            mask = torch.from_numpy(np.ascontiguousarray(mask))
+        m = mask.to(device=device).ne(0).to(torch.uint8).contiguous()
+        if tuple(m.shape) != tuple(p.shape):
+            raise ValueError(f"mask must be {tuple(p.shape)}, got {tuple(m.shape)}")
+    q = p.shape[0]
+    p16 = torch.empty((q, L.OBS_PAD), dtype=torch.float32, device=device)
+    ent = torch.empty((q,), dtype=torch.float32, device=device)
+    L.set_device(device)
+    L.check(L.lib().radar_kl_prepare_queries(L.ptr(p), L.ptr(m), q, L.NUM_OBS, eps, int(normalize), L.ptr(p16),
+                                             L.ptr(ent), L.current_stream_ptr(device)), "radar_kl_prepare_queries")
+    return p16, ent
+
+
+class RadarIndex:
+    """Exact flat index over (embedding, observation-probability) rows resident in HBM.
+
+    ``add`` / ``search`` / ``ntotal`` follow ``faiss.IndexFlatIP``; ``search`` additionally takes
+    ``query_probs``, ``mask``, ``alpha`` and ``mode``.
+    """
+
+    def __init__(self, d: int = 512, device: Union[str, torch.device] = "cuda", precision: str = "bf16",
+                 eps: float = 1e-8, normalize: bool = False, idx_offset: int = 0, algo: str = "auto",
+                 overfetch: int = 0, num_sms: int = 0, keep_bf16: bool = True):
+        self.d = int(d)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("RadarIndex runs on a CUDA device only (there is no CPU fallback)")
+        if precision not in L.PREC_BY_NAME:
+            raise ValueError(f"precision must be one of {sorted(L.PREC_BY_NAME)}")
+        if algo not in L.ALGO_BY_NAME:
+            raise ValueError(f"algo must be one of {sorted(L.ALGO_BY_NAME)}")
+        self.precision, self.algo = precision, algo
+        self.eps, self.normalize = float(eps), bool(normalize)
+        self.idx_offset = int(idx_offset)
+        self.overfetch, self.num_sms = int(overfetch), int(num_sms)
+        self.keep_bf16 = keep_bf16
+        self.emb_f32: Optional[torch.Tensor] = None
+        self.emb_bf16: Optional[torch.Tensor] = None
+        self.logq16: Optional[torch.Tensor] = None
+        self.klpack: Optional[torch.Tensor] = None
+        self.emb_max_norm = 0.0
+        self._workspace: Optional[torch.Tensor] = None
+        self.last_stats = SearchStats()
+        L.lib()  # fail loudly now if the extension is missing
+
+    # ---- faiss.IndexFlatIP surface ------------------------------------------------------------------
+    def __bool__(self) -> bool:  # dpr.py:310 tests truthiness of the index object
+        return True
+
+    @property
+    def ntotal(self) -> int:
+        if self.emb_f32 is not None:
+            return int(self.emb_f32.shape[0])
+        if self.logq16 is not None:
+            return int(self.logq16.shape[0])
+        return 0
+
+    def add(self, x: ArrayLike) -> None:
+        """Append embedding rows (float32[N,d]); ``faiss.IndexFlatIP.add`` (dpr.py:298)."""
+        x = _as_device_f32(x, self.device)
+        if x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError(f"expected [N,{self.d}] embeddings, got {tuple(x.shape)}")
+        if self.d % 4 != 0:
+            raise ValueError("embedding dim must be a multiple of 4")
+        n = x.shape[0]
+        if n == 0:
+            return
+        L.set_device(self.device)
+        bf16 = torch.empty((n, self.d), dtype=torch.bfloat16, device=self.device) if self.keep_bf16 else None
+        mx = torch.zeros((1,), dtype=torch.float32, device=self.device)
+        L.check(L.lib().radar_pack_embeddings(L.ptr(x), n, self.d, L.ptr(bf16), L.ptr(mx),
+                                              L.current_stream_ptr(self.device)), "radar_pack_embeddings")
+        self.emb_max_norm = max(self.emb_max_norm, float(mx.item()))
+        self.emb_f32 = x if self.emb_f32 is None else torch.cat([self.emb_f32, x], 0)
+        if self.keep_bf16:
+            self.emb_bf16 = bf16 if self.emb_bf16 is None else torch.cat([self.emb_bf16, bf16], 0)
+
+    def add_observations(self, probs: ArrayLike) -> None:
+        """Append observation-probability rows (float32[N,14], CheXpert-14 order) -- K1 corpus side."""
+        p = _as_device_f32(probs, self.device)
+        if p.dim() != 2 or p.shape[1] != L.NUM_OBS:
+            raise ValueError(f"expected [N,{L.NUM_OBS}] probabilities, got {tuple(p.shape)}")
+        n = p.shape[0]
+        if n == 0:
+            return
+        L.set_device(self.device)
+        logq = torch.empty((n, L.OBS_PAD), dtype=torch.float32, device=self.device)
+        pack = torch.empty((n, L.KLPACK), dtype=torch.bfloat16, device=self.device)
+        L.check(L.lib().radar_kl_prepare_corpus(L.ptr(p), n, L.NUM_OBS, self.eps, int(self.normalize), L.ptr(logq),
+                                                L.ptr(pack), L.current_stream_ptr(self.device)),
+                "radar_kl_prepare_corpus")
+        self.logq16 = logq if self.logq16 is None else torch.cat([self.logq16, logq], 0)
+        self.klpack = pack if self.klpack is None else torch.cat([self.klpack, pack], 0)
+
+    def reset(self) -> None:
+        self.emb_f32 = self.emb_bf16 = self.logq16 = self.klpack = None
+        self.emb_max_norm = 0.0
+
+    # ---- search -------------------------------------------------------------------------------------
+    def _corpus_struct(self, mode: int) -> L.CorpusStruct:
+        c = L.CorpusStruct()
+        c.n = self.ntotal
+        c.d = self.d
+        if mode != L.MODE_KL:
+            if self.emb_f32 is None:
+                raise RuntimeError("index holds no embeddings (call add) but mode needs them")
+            c.emb_f32 = L.ptr(self.emb_f32)
+            c.emb_bf16 = L.ptr(self.emb_bf16)
+        if mode != L.MODE_DPR:
+            if self.logq16 is None:
+                raise RuntimeError("index holds no observation probabilities (call add_observations)")
+            if self.emb_f32 is not None and self.logq16.shape[0] != self.emb_f32.shape[0]:
+                raise RuntimeError("embedding rows and observation rows differ in count")
+            c.logq16 = L.ptr(self.logq16)
+            c.klpack = L.ptr(self.klpack)
+        c.emb_max_norm = self.emb_max_norm
+        c.logq_max_abs = abs(math.log(self.eps)) * 1.0001
+        c.idx_offset = self.idx_offset
+        return c
+
+    def _get_workspace(self, nbytes: int) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty((nbytes + 256,), dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def resolve_mode(self, mode: Optional[str], have_emb: bool, have_probs: bool) -> int:
+        if mode is None:
+            if have_emb and have_probs and self.logq16 is not None and self.emb_f32 is not None:
+                return L.MODE_HYBRID
+            if have_emb and self.emb_f32 is not None:
+                return L.MODE_DPR
+            if have_probs:
+                return L.MODE_KL
+            raise ValueError("search needs query embeddings and/or query_probs")
+        if mode not in L.MODE_BY_NAME:
+            raise ValueError(f"mode must be one of {sorted(L.MODE_BY_NAME)}")
+        return L.MODE_BY_NAME[mode]
+
+    def search(self, x: Optional[ArrayLike], k: int, query_probs: Optional[ArrayLike] = None,
+               mask: Optional[ArrayLike] = None, alpha: float = 0.5, mode: Optional[str] = None,
+               precision: Optional[str] = None, algo: Optional[str] = None, collect_stats: bool = False,
+               prepared: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(scores float32[Q,k], ids int64[Q,k]) as CUDA tensors, best first.
+
+        DPR: inner products, descending (``IndexFlatIP.search``).  KL: KL(p_query||q_case), ascending.
+        hybrid: ``alpha*ip - (1-alpha)*KL``, descending.  Ties: smaller id first.
+        ``prepared`` = (p16, entropy) from :func:`prepare_queries` skips the query-side preparation.
+        """
+        m = self.resolve_mode(mode, x is not None, query_probs is not None or prepared is not None)
+        n = self.ntotal
+        if n == 0:
+            raise RuntimeError("search on an empty index")
+        if not (1 <= k <= L.MAX_K):
+            raise ValueError(f"k must be in [1,{L.MAX_K}], got {k}")
+        if k > n:
+            raise ValueError(f"k={k} exceeds ntotal={n}; clamp k in the caller (dpr.py:308)")
+        L.set_device(self.device)
+        qs = L.QueriesStruct()
+        xq = p16 = ent = None
+        if m != L.MODE_KL:
+            if x is None:
+                raise ValueError("query embeddings are required for dpr/hybrid")
+            xq = _as_device_f32(x, self.device)
+            if xq.dim() == 1:
+                xq = xq.unsqueeze(0)
+            if xq.shape[1] != self.d:
+                raise ValueError(f"query embeddings must be [Q,{self.d}], got {tuple(xq.shape)}")
+            qs.q = xq.shape[0]
+            qs.emb_f32 = L.ptr(xq)
+        if m != L.MODE_DPR:
+            if prepared is not None:
+                p16, ent = prepared
+            else:
+                if query_probs is None:
+                    raise ValueError("query_probs are required for kl/hybrid")
+                p16, ent = prepare_queries(query_probs, mask, self.device, self.eps, self.normalize)
+            if xq is not None and p16.shape[0] != xq.shape[0]:
+                raise ValueError("query embeddings and query_probs differ in row count")
+            qs.q = p16.shape[0]
+            qs.p16, qs.entropy = L.ptr(p16), L.ptr(ent)
+        q = int(qs.q)
+        out_s = torch.empty((q, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        if q == 0:
+            return out_s, out_i
+        cs = self._corpus_struct(m)
+        sp = L.SearchParams()
+        sp.mode, sp.k, sp.alpha = m, k, float(alpha)
+        sp.precision = L.PREC_BY_NAME[precision or self.precision]
+        sp.algo = L.ALGO_BY_NAME[algo or self.algo]
+        sp.overfetch, sp.num_sms = self.overfetch, self.num_sms
+        lib = L.lib()
+        nbytes = lib.radar_search_workspace_bytes(C.byref(cs), q, C.byref(sp))
+        if nbytes == 0:
+            L.check(1, "radar_search_workspace_bytes")
+        ws = self._get_workspace(int(nbytes))
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        stats = L.SearchStats() if collect_stats else None
+        rc = lib.radar_search(C.byref(cs), C.byref(qs), C.byref(sp), L.ptr(out_s), L.ptr(out_i), ws_ptr,
+                              ws.numel() - (ws_ptr - ws.data_ptr()), C.byref(stats) if stats else None,
+                              L.current_stream_ptr(self.device))
+        L.check(rc, "radar_search")
+        if stats is not None:
+            self.last_stats = SearchStats(stats.algo_used, stats.kernel_launches, int(stats.uncertified),
+                                          stats.parts, stats.kprime)
+        return out_s, out_i
+
+    def debug_filter_keys(self, x, query_probs=None, mask=None, alpha=0.5, mode=None) -> torch.Tensor:
+        """Dense [Q,N] dump of the tensor-core filter keys (bring-up aid; small problems only)."""
+        m = self.resolve_mode(mode, x is not None, query_probs is not None)
+        L.set_device(self.device)
+        qs = L.QueriesStruct()
+        keep = []
+        if m != L.MODE_KL:
+            xq = _as_device_f32(x, self.device)
+            qs.q, qs.emb_f32 = xq.shape[0], L.ptr(xq)
+            keep.append(xq)
+        if m != L.MODE_DPR:
+            p16, ent = prepare_queries(query_probs, mask, self.device, self.eps, self.normalize)
+            qs.q, qs.p16, qs.entropy = p16.shape[0], L.ptr(p16), L.ptr(ent)
+            keep += [p16, ent]
+        q = int(qs.q)
+        cs = self._corpus_struct(m)
+        sp = L.SearchParams()
+        sp.mode, sp.k, sp.alpha = m, min(10, self.ntotal), float(alpha)
+        sp.precision, sp.algo = L.PREC_BF16, L.ALGO_TC_FILTER
+        sp.num_sms = self.num_sms
+        out = torch.full((q, self.ntotal), float("nan"), dtype=torch.float32, device=self.device)
+        nbytes = L.lib().radar_search_workspace_bytes(C.byref(cs), q, C.byref(sp))
+        if nbytes == 0:
+            L.check(1, "radar_search_workspace_bytes")
+        ws = self._get_workspace(int(nbytes))
+        ws_ptr = (ws.data_ptr() + 255) // 256 * 256
+        L.check(L.lib().radar_debug_filter_keys(C.byref(cs), C.byref(qs), C.byref(sp), L.ptr(out), ws_ptr,
+                                                ws.numel() - (ws_ptr - ws.data_ptr()),
+                                                L.current_stream_ptr(self.device)), "radar_debug_filter_keys")
+        return out
+
+
+class GpuIndexFlatIP(RadarIndex):
+    """``faiss.IndexFlatIP`` spelling: numpy in, numpy out, missing results padded with -1 / -FLT_MAX."""
+
+    def __init__(self, d: int, device: Union[str, torch.device] = "cuda", precision: str = "fp32"):
+        super().__init__(d, device=device, precision=precision)
+
+    def search(self, x, k: int, **kw):  # type: ignore[override]
+        as_numpy = isinstance(x, np.ndarray)
+        nq = x.shape[0] if getattr(x, "ndim", 2) == 2 else 1
+        n = self.ntotal
+        kk = min(k, n)
+        dev_s = torch.full((nq, k), -torch.finfo(torch.float32).max, dtype=torch.float32, device=self.device)
+        dev_i = torch.full((nq, k), -1, dtype=torch.int64, device=self.device)
+        if kk > 0:
+            s, i = super().search(x, kk, **kw)
+            dev_s[:, :kk], dev_i[:, :kk] = s, i
+        if as_numpy:
+            return dev_s.cpu().numpy(), dev_i.cpu().numpy()
+        return dev_s, dev_i
+
+
+def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, ascending: bool
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of the union of per-shard lists; ``scores``/``ids`` are [parts, Q, k_in] CUDA tensors (the
+    layout an all-gather produces).  ``radar_merge_topk``."""
+    if scores.dim() != 3 or scores.shape != ids.shape:
+        raise ValueError("scores/ids must be [parts, Q, k_in] with equal shapes")
+    if scores.device.type != "cuda":
+        raise RuntimeError("merge_topk runs on a CUDA device only (there is no CPU fallback)")
+    parts, q, k_in = scores.shape
+    scores = scores.contiguous().float()
+    ids = ids.contiguous().long()
+    out_s = torch.empty((q, k), dtype=torch.float32, device=scores.device)
+    out_i = torch.empty((q, k), dtype=torch.int64, device=scores.device)
+    L.set_device(scores.device)
+    L.check(L.lib().radar_merge_topk(L.ptr(scores), L.ptr(ids), q, parts, k_in, k, int(ascending), L.ptr(out_s),
+                                     L.ptr(out_i), L.current_stream_ptr(scores.device)), "radar_merge_topk")
+    return out_s, out_i
+
+
+def project_normalize(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """``F.normalize(F.linear(x, weight, bias), dim=-1)`` (dpr.py:246 / :263) as one CUDA kernel."""
+    if x.device.type != "cuda":
+        raise RuntimeError("project_normalize runs on a CUDA device only")
+    x = x.contiguous().float()
+    w = weight.detach().contiguous().float()
+    b = None if bias is None else bias.detach().contiguous().float()
+    y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+    L.set_device(x.device)
+    L.check(L.lib().radar_project_normalize(L.ptr(x), L.ptr(w), L.ptr(b), x.shape[0], x.shape[1], w.shape[0],
+                                            L.ptr(y), L.current_stream_ptr(x.device)), "radar_project_normalize")
+    return y

@@ -1,0 +1,501 @@
+"""GPU parity tests (``-m gpu``): every call goes through the C ABI of libradar_retrieval.so and is compared
+with the oracle on the same seeded inputs.
+
+  * fp32 precision, either algorithm: ids AND scores bit-identical to the canonical C oracle;
+  * bf16 precision: recall@k >= 0.999 against fp32 and returned scores bit-identical to the canonical score
+    of the returned ids;
+  * golden fixtures (float64 oracle) and fixtures produced by the reference itself;
+  * at BASELINE.json's full sizes: agreement of the two independent algorithms + sampled oracle checks.
+Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits_to_f32, make_problem
+
+pytestmark = pytest.mark.gpu
+
+MODES = {"dpr": 0, "kl": 1, "hybrid": 2}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    return torch.device("cuda:0")
+
+
+def _oracle(p, mode, k, alpha=0.5, masked=True, normalize=False, idx_offset=0):
+    from oracle import c_oracle as co
+    logq = co.prepare_corpus(p["c_pr"], normalize=normalize)
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"] if masked else None, normalize=normalize)
+    return co.search(MODES[mode], k, q_emb=p["q_emb"], p16=p16, entropy=ent, c_emb=p["c_emb"], logq16=logq,
+                     alpha=alpha, idx_offset=idx_offset)
+
+
+def _index(p, dev, **kw):
+    from radar_multimodal_radiology_b200.index import RadarIndex
+    idx = RadarIndex(p["c_emb"].shape[1], device=dev, **kw)
+    idx.add(p["c_emb"])
+    idx.add_observations(p["c_pr"])
+    return idx
+
+
+def _search(idx, p, mode, k, alpha=0.5, masked=True, **kw):
+    s, i = idx.search(None if mode == "kl" else p["q_emb"], k, query_probs=None if mode == "dpr" else p["q_pr"],
+                      mask=p["mask"] if (masked and mode != "dpr") else None, alpha=alpha, mode=mode,
+                      collect_stats=True, **kw)
+    torch.cuda.synchronize()
+    return s.cpu().numpy(), i.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------
+# preparation kernels
+# ---------------------------------------------------------------------------------------------------
+def test_prepare_kernels_match_oracle_bit_for_bit(dev):
+    from oracle import c_oracle as co
+    from radar_multimodal_radiology_b200.index import prepare_queries
+    p = make_problem(5000, 777, seed=1)
+    p["c_pr"][0] = 0.0
+    p["c_pr"][1] = 1.0
+    p["q_pr"][0, :5] = 0.0
+    for normalize in (False, True):
+        if normalize:
+            p["c_pr"][0, 3] = 0.25
+        idx = _index(p, dev, normalize=normalize)
+        want = co.prepare_corpus(p["c_pr"], normalize=normalize)
+        got = idx.logq16.cpu().numpy()
+        assert np.array_equal(got, want)
+        pack = idx.klpack.float().cpu().numpy()
+        assert np.array_equal(pack[:, :16], torch.from_numpy(want).bfloat16().float().numpy())
+        assert np.max(np.abs(pack[:, :16] + pack[:, 16:] - want)) <= 2.0 ** -16 * 18.5
+        for mask in (None, p["mask"]):
+            p16, ent = prepare_queries(p["q_pr"], mask, dev, normalize=normalize)
+            w16, went = co.prepare_queries(p["q_pr"], mask, normalize=normalize)
+            assert np.array_equal(p16.cpu().numpy(), w16) and np.array_equal(ent.cpu().numpy(), went)
+    assert torch.equal(idx.emb_bf16.cpu(), torch.from_numpy(p["c_emb"]).bfloat16())
+    true_max = float(np.linalg.norm(p["c_emb"].astype(np.float64), axis=1).max())
+    assert true_max <= idx.emb_max_norm <= true_max * 1.0001
+
+
+# ---------------------------------------------------------------------------------------------------
+# exact CUDA-core scan: bit-exact against the canonical oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,n,q", [("kl", 10000, 1000), ("dpr", 6000, 300), ("hybrid", 6000, 300)])
+@pytest.mark.parametrize("k", [1, 10, 32, 128])
+def test_simt_exact_is_bit_identical_to_oracle(dev, mode, n, q, k):
+    """BASELINE config 1 (KL, 10k cases, 1k queries, top-k=10) and its DPR / hybrid siblings."""
+    p = make_problem(n, q, seed=2)
+    idx = _index(p, dev, precision="fp32", algo="simt")
+    s, i = _search(idx, p, mode, k)
+    ws, wi = _oracle(p, mode, k)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    assert idx.last_stats.algo_used == 1 and idx.last_stats.kernel_launches == 3
+
+
+@pytest.mark.parametrize("algo,precision", [("simt", "fp32"), ("tc", "fp32"), ("tc", "bf16")])
+def test_golden_vectors(dev, golden, algo, precision):
+    """float64-oracle fixtures; inputs are bf16-representable so every precision must return the same ids
+    (up to the KL cancellation band) and scores within the stated tolerances."""
+    from oracle import retrieval_oracle as ro
+    g = golden
+    p = dict(c_emb=g["c_emb"], q_emb=g["q_emb"], c_pr=g["c_probs"], q_pr=g["q_probs"], mask=g["mask"])
+    idx = _index(p, dev, precision=precision, algo=algo)
+    for k in (1, 10, 32):
+        s, i = _search(idx, p, "dpr", k)
+        assert np.array_equal(i, g[f"dpr_k{k}_i"])
+        assert np.max(np.abs(s - g[f"dpr_k{k}_s"])) <= 1e-5 * np.abs(g[f"dpr_k{k}_s"]).max()  # 1e-5 relative
+        for tag, masked in (("kl", False), ("klmask", True)):
+            s, i = _search(idx, p, "kl", k, masked=masked)
+            want_s, want_i = g[f"{tag}_k{k}_s"], g[f"{tag}_k{k}_i"]
+            scale = ro.kl_operand_scale_fp64(g["q_probs"], g["c_probs"], g["mask"] if masked else None)
+            tol = 1e-5 * np.take_along_axis(scale, want_i, axis=1)  # SURVEY.md section 8c tolerance
+            assert np.all(np.abs(s - want_s) <= tol + 1e-12)
+            assert np.mean(i == want_i) > 0.97
+        for alpha in (0.0, 0.25, 0.5, 1.0):
+            tag = f"hyb_a{int(alpha * 100):03d}_k{k}"
+            s, i = _search(idx, p, "hybrid", k, alpha=alpha)
+            assert np.mean(i == g[tag + "_i"]) > 0.97
+            assert np.max(np.abs(s - g[tag + "_s"])) <= 2e-4
+
+
+def test_normalize_option(dev, golden):
+    g = golden
+    p = dict(c_emb=g["c_emb"], q_emb=g["q_emb"], c_pr=g["c_probs"], q_pr=g["q_probs"], mask=g["mask"])
+    idx = _index(p, dev, precision="fp32", algo="simt", normalize=True)
+    s, i = _search(idx, p, "kl", 10, masked=False)
+    assert np.mean(i == g["klnorm_k10_i"]) > 0.97 and np.max(np.abs(s - g["klnorm_k10_s"])) < 1e-4
+    assert i[0, 0] == 5 and abs(s[0, 0]) < 1e-6 and np.all(s >= -1e-6)  # categorical KL >= 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases (the reference tests none; these are the ones its API admits)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("n,q,k", [(1, 1, 1), (5, 3, 5), (63, 1, 10), (64, 65, 64), (129, 130, 7), (1000, 257, 128)])
+def test_ragged_and_tiny_shapes(dev, algo, n, q, k):
+    p = make_problem(n, q, seed=4)
+    idx = _index(p, dev, precision="fp32", algo=algo)
+    for mode in ("dpr", "kl", "hybrid"):
+        s, i = _search(idx, p, mode, k)
+        ws, wi = _oracle(p, mode, k)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws), (mode, n, q, k)
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+def test_duplicate_rows_tie_break_by_smaller_id(dev, algo):
+    p = make_problem(400, 9, seed=6)
+    p["c_emb"][100:300] = p["c_emb"][7]      # 200 identical rows (plus row 7 itself)
+    p["c_pr"][100:300] = p["c_pr"][7]
+    p["q_emb"][0] = p["c_emb"][7]
+    idx = _index(p, dev, precision="fp32", algo=algo)
+    for mode in ("dpr", "hybrid", "kl"):
+        s, i = _search(idx, p, mode, 64)
+        ws, wi = _oracle(p, mode, 64)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    s, i = _search(idx, p, "dpr", 64)
+    assert i[0, 0] == 7 and i[0, 1:].tolist() == list(range(100, 163))
+
+
+def test_argument_errors_raise(dev):
+    p = make_problem(50, 4)
+    idx = _index(p, dev)
+    with pytest.raises(ValueError, match="exceeds ntotal"):
+        idx.search(p["q_emb"], 51, mode="dpr")
+    with pytest.raises(ValueError, match="k must be"):
+        idx.search(p["q_emb"], 0, mode="dpr")
+    with pytest.raises(ValueError, match="query embeddings must be"):
+        idx.search(p["q_emb"][:, :64], 5, mode="dpr")
+    with pytest.raises(ValueError):
+        idx.search(p["q_emb"], 5, query_probs=p["q_pr"][:2], mode="hybrid")
+    from radar_multimodal_radiology_b200.index import RadarIndex
+    empty = RadarIndex(512, device=dev)
+    assert empty.ntotal == 0 and bool(empty)
+    with pytest.raises(RuntimeError, match="empty index"):
+        empty.search(p["q_emb"], 1, mode="dpr")
+    s, i = idx.search(p["q_emb"][:0], 5, mode="dpr")
+    assert s.shape == (0, 5) and i.shape == (0, 5)
+    # tensor-core path refuses shapes it cannot take instead of silently switching algorithm
+    odd = RadarIndex(96, device=dev, algo="tc")
+    odd.add(np.ones((10, 96), np.float32))
+    with pytest.raises(RuntimeError, match="RADAR_ALGO_TC_FILTER"):
+        odd.search(np.ones((1, 96), np.float32), 3, mode="dpr")
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("num_sms", [1, 7, 148, 1000])
+def test_result_independent_of_slab_count(dev, algo, num_sms):
+    """num_sms drives how many corpus slabs a query tile is split into; the merge must hide it."""
+    p = make_problem(9000, 70, seed=8)
+    idx = _index(p, dev, precision="fp32", algo=algo, num_sms=num_sms)
+    for mode in ("hybrid", "kl"):
+        s, i = _search(idx, p, mode, 10)
+        ws, wi = _oracle(p, mode, 10)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    if num_sms >= 148:
+        assert idx.last_stats.parts > 1
+
+
+def test_embedding_dims_other_than_512(dev):
+    for d, algo in ((64, "tc"), (256, "tc"), (128, "simt"), (100, "simt")):
+        p = make_problem(700, 33, d=d, seed=9)
+        idx = _index(p, dev, precision="fp32", algo=algo)
+        s, i = _search(idx, p, "hybrid", 10)
+        ws, wi = _oracle(p, "hybrid", 10)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws), d
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core filter
+# ---------------------------------------------------------------------------------------------------
+def test_tc_filter_keys_match_bf16_products(dev):
+    """Dense dump of the tcgen05 accumulators against the same bf16-rounded products in float64."""
+    from oracle import c_oracle as co
+    p = make_problem(1000, 150, seed=10)
+    idx = _index(p, dev)
+    bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).bfloat16().double().numpy()
+    ip = bf(p["q_emb"]) @ bf(p["c_emb"]).T
+    keys = idx.debug_filter_keys(p["q_emb"], mode="dpr").cpu().numpy()
+    assert np.isfinite(keys).all() and np.max(np.abs(keys - ip)) < 2e-5
+    logq = co.prepare_corpus(p["c_pr"]).astype(np.float64)
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"])
+    kl_key = p16.astype(np.float64) @ logq.T - ent.astype(np.float64)[:, None]
+    keys = idx.debug_filter_keys(None, query_probs=p["q_pr"], mask=p["mask"], mode="kl").cpu().numpy()
+    assert np.max(np.abs(keys - kl_key)) < 2e-4
+    a = 0.5
+    hyb = (bf(a * p["q_emb"]) @ bf(p["c_emb"]).T) + (1 - a) * kl_key
+    keys = idx.debug_filter_keys(p["q_emb"], query_probs=p["q_pr"], mask=p["mask"], alpha=a, mode="hybrid").cpu().numpy()
+    assert np.max(np.abs(keys - hyb)) < 2e-4
+
+
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+@pytest.mark.parametrize("k", [1, 10, 32, 85])
+def test_tc_fp32_mode_is_certified_bit_identical(dev, mode, k):
+    p = make_problem(30000, 500, seed=12)
+    idx = _index(p, dev, precision="fp32", algo="tc")
+    s, i = _search(idx, p, mode, k)
+    ws, wi = _oracle(p, mode, k)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    st = idx.last_stats
+    assert st.algo_used == 2
+    assert st.uncertified <= 0.25 * 500, f"certificate failed for {st.uncertified}/500 queries: filter is too loose"
+
+
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+@pytest.mark.parametrize("k", [10, 32])
+def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
+    """bf16 tolerance statement: ids have recall@k >= 0.999 against the fp32 result; every returned score is
+    the canonical fp32 score of the returned id (the filter only selects, it never scores)."""
+    from oracle import c_oracle as co
+    p = make_problem(50000, 1200, seed=13)
+    idx = _index(p, dev, precision="bf16", algo="tc")
+    s, i = _search(idx, p, mode, k)
+    ws, wi = _oracle(p, mode, k)
+    recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)])
+    assert recall >= 0.999, recall
+    logq = co.prepare_corpus(p["c_pr"])
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"] if mode != "dpr" else None)
+    canon = co.score_pairs(MODES[mode], i, q_emb=p["q_emb"], p16=p16, entropy=ent, c_emb=p["c_emb"], logq16=logq)
+    assert np.array_equal(s, canon)
+    assert idx.last_stats.uncertified == 0  # no certificate / fallback in bf16 mode
+
+
+# ---------------------------------------------------------------------------------------------------
+# merge / re-rank / projection kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("parts,k_in,k_out,ascending", [(2, 10, 10, False), (8, 32, 32, False), (8, 32, 5, True),
+                                                        (3, 1, 3, True), (8, 128, 128, False)])
+def test_merge_kernel_matches_oracle(dev, parts, k_in, k_out, ascending):
+    from oracle import c_oracle as co
+    from radar_multimodal_radiology_b200.index import merge_topk
+    rng = np.random.default_rng(parts * 100 + k_in)
+    q = 333
+    s = rng.standard_normal((parts, q, k_in)).astype(np.float32)
+    s[:, :, ::3] = np.round(s[:, :, ::3], 1)  # plenty of cross-shard ties
+    i = rng.permutation(parts * q * k_in).reshape(parts, q, k_in).astype(np.int64)
+    i[0, :, -1] = -1  # padding entries of a short shard
+    ws, wi = co.merge_topk(s, i, k_out, ascending)
+    gs, gi = merge_topk(torch.from_numpy(s).to(dev), torch.from_numpy(i).to(dev), k_out, ascending)
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gs.cpu().numpy(), ws)
+
+
+def test_sharded_index_world1_and_simulated_shards(dev):
+    """Row shards searched one after another on one GPU + the merge kernel == one unsharded search."""
+    from radar_multimodal_radiology_b200.index import RadarIndex, merge_topk
+    from radar_multimodal_radiology_b200.sharded import ShardedRadarIndex, shard_bounds
+    p = make_problem(10007, 200, seed=14)
+    ws, wi = _oracle(p, "hybrid", 32)
+    sh = ShardedRadarIndex(512, device=dev, precision="fp32").build(10007, p["c_emb"], p["c_pr"])
+    s, i = sh.search(torch.from_numpy(p["q_emb"]), 32, query_probs=p["q_pr"], mask=p["mask"], mode="hybrid")
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+    for world in (2, 8):
+        ss, ii = [], []
+        for r in range(world):
+            lo, hi = shard_bounds(10007, world, r)
+            idx = RadarIndex(512, device=dev, precision="fp32", idx_offset=lo)
+            idx.add(p["c_emb"][lo:hi])
+            idx.add_observations(p["c_pr"][lo:hi])
+            s, i = idx.search(p["q_emb"], 32, query_probs=p["q_pr"], mask=p["mask"], mode="hybrid")
+            ss.append(s)
+            ii.append(i)
+        ms, mi = merge_topk(torch.stack(ss), torch.stack(ii), 32, ascending=False)
+        assert np.array_equal(mi.cpu().numpy(), wi) and np.array_equal(ms.cpu().numpy(), ws)
+
+
+def test_rerank_and_gather_kernels_match_reference_fixtures(dev, ref_fixtures):
+    from oracle import retrieval_oracle as ro
+    from radar_multimodal_radiology_b200.iterative_rag import gather_case_bits, rerank_overlap
+    vocab = ref_fixtures["default_vocab"]
+    for case in ref_fixtures["rank_retrieved_passages"]:
+        if not case["passages"] or not case["missing"]:
+            continue
+        # bitmask form over the detector's own vocabulary order (the kernel is vocabulary-agnostic)
+        case_bits = [ro.observation_bits(ro.detect_observations(t, vocab), vocab) for t in case["passages"]]
+        miss = ro.observation_bits(case["missing"], vocab)
+        sc, order = rerank_overlap(torch.tensor([case_bits], dtype=torch.int16, device=dev),
+                                   torch.tensor([miss], dtype=torch.int16, device=dev))
+        sc, order = sc.cpu().numpy()[0], order.cpu().numpy()[0]
+        got = [[case["passages"][j], float(sc[j])] for j in order]
+        assert got == case["ranked"]  # same passages, same order, same float64 scores as the reference
+    rng = np.random.default_rng(3)
+    q, k = 1000, 32
+    cb = rng.integers(0, 1 << 14, (q, k)).astype(np.int16)
+    mb = rng.integers(0, 1 << 14, q).astype(np.int16)
+    mb[:10] = 0
+    sc, order = rerank_overlap(torch.from_numpy(cb).to(dev), torch.from_numpy(mb).to(dev))
+    want = ro.rerank_scores_bits(cb, mb)
+    assert np.array_equal(sc.cpu().numpy(), want)
+    assert np.array_equal(order.cpu().numpy(), np.argsort(-want, axis=1, kind="stable"))
+    table = rng.integers(0, 1 << 14, 5000).astype(np.int16)
+    ids = rng.integers(0, 5000, (q, k)).astype(np.int64)
+    ids[0, 0] = -1
+    got = gather_case_bits(torch.from_numpy(table).to(dev), torch.from_numpy(ids).to(dev)).cpu().numpy()
+    want_g = table[np.maximum(ids, 0)]
+    want_g[0, 0] = 0
+    assert np.array_equal(got, want_g)
+
+
+def test_project_normalize_kernel_matches_torch(dev):
+    from radar_multimodal_radiology_b200.index import project_normalize
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(768, 512).to(dev)
+    x = torch.randn(300, 768, device=dev)
+    want = torch.nn.functional.normalize(lin(x), dim=-1)
+    got = project_normalize(x, lin.weight, lin.bias)
+    assert torch.allclose(got, want, atol=1e-5, rtol=0)
+    assert torch.allclose(got.norm(dim=1), torch.ones(300, device=dev), atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference-facing Python API
+# ---------------------------------------------------------------------------------------------------
+def test_hybrid_retriever_reproduces_the_reference_run(dev, ref_fixtures):
+    """Same passages, embeddings and queries as the fixture the reference produced (with a stand-in faiss):
+    same passages in the same order, scores within 1e-6."""
+    from radar_multimodal_radiology_b200.dense_passage_retrieval import HybridRetriever, RetrievalConfig
+    fx = ref_fixtures["hybrid_retriever"]
+    emb = bits_to_f32(np.array(fx["embeddings_bf16_bits"], dtype=np.uint16))
+    queries = bits_to_f32(np.array(fx["queries_bf16_bits"], dtype=np.uint16))
+    passages = [f"passage {i}" for i in range(fx["n"])]
+    for precision in ("fp32", "bf16"):
+        hr = HybridRetriever(RetrievalConfig(), embedder=None, precision=precision)
+        hr.build_indices(passages, [[] for _ in passages], embeddings=emb)
+        assert hr.semantic_index and hr.semantic_index.ntotal == fx["n"]
+        for run in fx["retrieve"]:
+            got_p, got_s = hr.retrieve(torch.from_numpy(queries[run["query"]]).to(dev), run["k"])
+            assert got_p == run["passages"]
+            assert all(isinstance(x, str) for x in got_p) and all(isinstance(x, float) for x in got_s)
+            assert np.allclose(got_s, run["scores"], rtol=0, atol=1e-6)
+        hn = hr.retrieve_with_hard_negatives(torch.from_numpy(queries[0]))
+        want = fx["hard_negatives_default"]
+        assert hn["positives"] == want["positives"] and hn["negatives"] == want["negatives"]
+        assert np.allclose(hn["positive_scores"], want["positive_scores"], atol=1e-6)
+        assert np.allclose(hn["negative_scores"], want["negative_scores"], atol=1e-6)
+        hn2 = hr.retrieve_with_hard_negatives(torch.from_numpy(queries[1]), k=4, num_negatives=2)
+        assert hn2["positives"] == fx["hard_negatives_k4_n2"]["positives"]
+        assert hn2["negatives"] == fx["hard_negatives_k4_n2"]["negatives"]
+    empty = HybridRetriever(RetrievalConfig(), embedder=None)
+    empty.build_indices([], [])
+    assert empty.retrieve(torch.from_numpy(queries[0]), 5) == (fx["empty_index"]["passages"], fx["empty_index"]["scores"])
+
+
+def test_dense_passage_retrieval_end_to_end_and_rag_seam(dev):
+    """The reference's own smoke sequence (dpr.py:358-391, test_2.py:53-89) against the drop-in."""
+    from annotate_retrieve.modeling_dense_passage_retrieval import create_dpr_model, make_retrieval_function
+    from annotate_retrieve.modeling_iterative_rag import create_iterative_rag_model
+    names = ["Cardiomegaly", "Pneumonia", "Edema", "Atelectasis", "Pleural Effusion"]
+    passages = [f"Report {i}: findings of {names[i % 5]} and {names[(i * 3 + 1) % 5]}." for i in range(50)]
+    observations = [[names[i % 5], names[(i * 3 + 1) % 5]] for i in range(50)]
+    dpr = create_dpr_model()
+    dpr.build_retrieval_database(passages, observations)
+    assert dpr.retriever.semantic_index.ntotal == 50 and dpr.retriever.case_bits.shape == (50,)
+    for query in ["cardiomegaly", "pneumonia", "chest findings"]:
+        retrieved, scores = dpr.retrieve_for_text(query, k=5)
+        assert len(retrieved) == 5 and len(scores) == 5 and all(p in passages for p in retrieved)
+        assert scores == sorted(scores, reverse=True) and all(-1.0001 <= s <= 1.0001 for s in scores)
+    r2, s2 = dpr.retrieve_for_text(passages[17], k=1)
+    assert r2 == [passages[17]] and s2[0] > 0.999  # a passage retrieves itself
+    assert len(dpr.retrieve_for_text("x")[0]) == 5 and len(dpr.retrieve_for_text("x", k=500)[0]) == 50
+    img = torch.zeros(3, 224, 224)
+    assert len(dpr.retrieve_for_image(img, k=5)[0]) == 5
+    hn = dpr.retriever.retrieve_with_hard_negatives(dpr.embedder.encode_text(["edema"]).squeeze(0))
+    assert len(hn["positives"]) == 5 and len(hn["negatives"]) == 3
+    rag = create_iterative_rag_model()
+    seen = []
+    fn = make_retrieval_function(dpr)
+    res = rag.generate_with_iterative_retrieval(
+        "Initial findings", lambda q, k: (seen.append((q, k)) or fn(q, k)), lambda ctx: f"Generated: {ctx[:40]}",
+        reference_text="Reference with Cardiomegaly and Atelectasis")
+    assert len(seen) == 3 and all(k == 5 for _, k in seen) and res["iterations"] == 3
+    assert len(res["retrieved_passages"]) == 15 and all(p in passages for p in res["retrieved_passages"])
+
+
+def test_batched_retrieval_round_matches_per_case_oracle(dev):
+    """BASELINE config 5 in miniature: masked re-retrieval for a batch of cases + bitmask re-rank."""
+    from oracle import retrieval_oracle as ro
+    from radar_multimodal_radiology_b200 import synthetic as syn
+    from radar_multimodal_radiology_b200.iterative_rag import batched_retrieval_round
+    p = make_problem(20000, 400, seed=15)
+    idx = _index(p, dev, precision="fp32")
+    rng = np.random.default_rng(5)
+    table = rng.integers(0, 1 << 14, 20000).astype(np.int16)
+    for rnd in range(3):
+        mask = syn.observation_masks(400, rnd)
+        bits = syn.mask_to_bits(mask)
+        out = batched_retrieval_round(idx, torch.from_numpy(p["q_emb"]).to(dev), torch.from_numpy(p["q_pr"]).to(dev),
+                                      bits.to(dev), torch.from_numpy(table).to(dev), k=5, alpha=0.5, mode="hybrid")
+        pp = dict(p, mask=mask.numpy())
+        ws, wi = _oracle(pp, "hybrid", 5)
+        assert np.array_equal(out["ids"].cpu().numpy(), wi) and np.array_equal(out["scores"].cpu().numpy(), ws)
+        want_rr = ro.rerank_scores_bits(table[wi], bits.numpy())
+        assert np.array_equal(out["rerank_scores"].cpu().numpy(), want_rr)
+
+
+def test_kl_retriever_package(dev):
+    from src.knowledge import ObservationKLRetriever
+    p = make_problem(3000, 40, seed=16)
+    r = ObservationKLRetriever(device=dev).build(p["c_pr"])
+    kl, ids = r.search(p["q_pr"], k=10)
+    ws, wi = _oracle(p, "kl", 10, masked=False)
+    assert np.array_equal(ids.cpu().numpy(), wi) and np.array_equal(kl.cpu().numpy(), ws)
+    one_ids, one_kl = r.retrieve(p["q_pr"][0], k=3)
+    assert one_ids == wi[0, :3].tolist() and one_kl == [float(v) for v in ws[0, :3]]
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json sizes: independent algorithms agree; sampled oracle check
+# ---------------------------------------------------------------------------------------------------
+def _big_problem(n, q, dev, need_emb, need_probs):
+    from radar_multimodal_radiology_b200 import synthetic as syn
+    out = {}
+    if need_emb:
+        out["c_emb"] = syn.embeddings(n, 512, syn.SEED_CORPUS_EMB, dev)
+        out["q_emb"] = syn.query_embeddings(q, out["c_emb"])
+    if need_probs:
+        out["c_pr"] = syn.observation_probs(n, syn.SEED_CORPUS_PROBS, dev)
+        out["q_pr"] = syn.observation_probs(q, syn.SEED_QUERY_PROBS, dev)
+    return out
+
+
+def test_config2_kl_377k_cases_64k_queries(dev):
+    """KL at MIMIC-CXR scale (BASELINE config 2): tcgen05 filter (fp32-certified) vs exact scan on all 65 536
+    queries, plus 48 queries against the CPU oracle."""
+    from oracle import c_oracle as co
+    from radar_multimodal_radiology_b200.index import RadarIndex
+    n, q, k = 377000, 65536, 10
+    t = _big_problem(n, q, dev, False, True)
+    idx = RadarIndex(512, device=dev, precision="fp32")
+    idx.add_observations(t["c_pr"])
+    s_tc, i_tc = idx.search(None, k, query_probs=t["q_pr"], mode="kl", algo="tc", collect_stats=True)
+    unc = idx.last_stats.uncertified
+    s_ex, i_ex = idx.search(None, k, query_probs=t["q_pr"], mode="kl", algo="simt")
+    assert torch.equal(i_tc, i_ex) and torch.equal(s_tc, s_ex)
+    assert unc < 0.05 * q
+    assert bool((s_tc[:, 1:] >= s_tc[:, :-1]).all())  # ascending KL
+    sel = np.linspace(0, q - 1, 48).astype(int)
+    logq = idx.logq16.cpu().numpy()
+    p16, ent = co.prepare_queries(t["q_pr"][sel].cpu().numpy())
+    ws, wi = co.search(co.MODE_KL, k, p16=p16, entropy=ent, logq16=logq)
+    assert np.array_equal(i_tc[sel].cpu().numpy(), wi) and np.array_equal(s_tc[sel].cpu().numpy(), ws)
+
+
+def test_config3_dpr_377k_corpus_64k_queries(dev):
+    """BiomedCLIP-shaped DPR (BASELINE config 3): bf16 filter on all 65 536 queries; recall against the exact
+    scan on 4 096 of them; 32 queries against the CPU oracle."""
+    from oracle import c_oracle as co
+    from radar_multimodal_radiology_b200.index import RadarIndex
+    n, q, k = 377000, 65536, 10
+    t = _big_problem(n, q, dev, True, False)
+    idx = RadarIndex(512, device=dev, precision="bf16")
+    idx.add(t["c_emb"])
+    s_tc, i_tc = idx.search(t["q_emb"], k, mode="dpr", algo="tc")
+    assert bool((s_tc[:, 1:] <= s_tc[:, :-1]).all())
+    sub = torch.arange(0, q, 16, device=dev)
+    s_ex, i_ex = idx.search(t["q_emb"][sub], k, mode="dpr", algo="simt", precision="fp32")
+    inter = (i_tc[sub].unsqueeze(2) == i_ex.unsqueeze(1)).any(2).float().mean().item()
+    assert inter >= 0.999, inter
+    s_ct, i_ct = idx.search(t["q_emb"][sub], k, mode="dpr", algo="tc", precision="fp32", collect_stats=True)
+    assert torch.equal(i_ct, i_ex) and torch.equal(s_ct, s_ex)
+    sel = sub[:32].cpu().numpy()
+    ws, wi = co.search(co.MODE_DPR, k, q_emb=t["q_emb"][sel].cpu().numpy(), c_emb=t["c_emb"].cpu().numpy())
+    assert np.array_equal(i_ex[:32].cpu().numpy(), wi) and np.array_equal(s_ex[:32].cpu().numpy(), ws)
