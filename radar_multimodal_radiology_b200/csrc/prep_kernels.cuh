@@ -154,9 +154,10 @@ __global__ void __launch_bounds__(128) rerank_overlap_kernel(const uint16_t* __r
         double sc = 0.5;
         if (m > 0) {
             const double overlap = static_cast<double>(__popc(case_bits[r * k + j] & mb));
-            const double cover = overlap / (static_cast<double>(m) + 1e-8);
-            const double div = fmin(overlap / static_cast<double>(m), 1.0) * 0.2;
-            sc = cover + div;
+            // explicit _rn intrinsics: no fma contraction, so the float64 result equals CPython's
+            const double cover = __ddiv_rn(overlap, __dadd_rn(static_cast<double>(m), 1e-8));
+            const double div = __dmul_rn(fmin(__ddiv_rn(overlap, static_cast<double>(m)), 1.0), 0.2);
+            sc = __dadd_rn(cover, div);
         }
         s[j] = sc;
         o[j] = j;
