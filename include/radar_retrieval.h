@@ -102,7 +102,7 @@ typedef struct radar_search_params {
     float alpha;       /* hybrid weight (RetrievalConfig.hybrid_alpha, dpr.py:187); ignored unless HYBRID */
     int32_t overfetch; /* candidates re-scored per query on the filter path; 0 = automatic */
     int32_t num_sms;   /* 0 = all SMs of the device (tests use small values to force multi-part merges) */
-    int32_t reserved;
+    int32_t reserved;  /* flags; bit 0: tensor-core filter uses single CTAs instead of cta_group::2 pairs */
 } radar_search_params_t;
 
 /* Per-call statistics written to HOST memory when the pointer is non-NULL (forces a stream sync). */
@@ -124,10 +124,12 @@ int radar_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * point when the process drives more than one GPU; one process per GPU under torchrun needs it once). */
 int radar_set_device(int device);
 
-/* measurement aid: the next radar_search calls of this thread record the two cudaEvent_t (created by the
- * caller; NULL disables) immediately before / after the dominant kernel (scan or tensor-core filter) on
- * the call's stream, so that a benchmark can time that kernel alone without a profiler. */
-int radar_set_profile_events(void* ev_start, void* ev_stop);
+/* measurement aid: while enabled, every radar_search call of this thread records a pair of CUDA events
+ * (owned by the library) immediately before / after its dominant kernel (exact scan or tensor-core
+ * filter) on the call's stream; radar_profile_kernel_ms waits for the last pair and returns the elapsed
+ * milliseconds (host output), so a benchmark can time that kernel alone without a profiler. */
+int radar_profile_enable(int enable);
+int radar_profile_kernel_ms(float* ms_out);
 
 /* ---- index build (replaces IndexFlatIP.add, dpr.py:298; K1 corpus side) ------------------------- */
 

@@ -59,7 +59,7 @@ class SearchStats(C.Structure):
 
 EXPORTS = [
     "radar_last_error", "radar_abi_version", "radar_device_info", "radar_set_device",
-    "radar_set_profile_events", "radar_pack_embeddings",
+    "radar_profile_enable", "radar_profile_kernel_ms", "radar_pack_embeddings",
     "radar_kl_prepare_corpus", "radar_kl_prepare_queries", "radar_search_workspace_bytes", "radar_search",
     "radar_debug_filter_keys", "radar_merge_topk", "radar_rerank_overlap", "radar_gather_bits",
     "radar_project_normalize",
@@ -128,7 +128,8 @@ def lib():
         l.radar_project_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p]
         l.radar_set_device.argtypes = [C.c_int]
-        l.radar_set_profile_events.argtypes = [C.c_void_p, C.c_void_p]
+        l.radar_profile_enable.argtypes = [C.c_int]
+        l.radar_profile_kernel_ms.argtypes = [C.POINTER(C.c_float)]
         l.radar_device_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         for name in EXPORTS:
             getattr(l, name)  # raises AttributeError if a declared symbol is not exported

@@ -56,11 +56,12 @@ struct Plan {
     int kp;            // candidates a compaction keeps (k on the exact path, k' on the filter path)
     int R;             // candidates selected per query for re-scoring (= kp)
     int64_t q_tiles;   // query tiles of the main pass
-    int tile_q;        // rows per query tile (64 scan / 128 filter)
+    int tile_q;        // rows per query tile (64 scan / 128 or 256 filter)
+    int ncta;          // CTAs per filter work tile (2 = cta_group::2 pairs)
     int parts;
     int64_t rows_per_part;
     // workspace offsets (bytes)
-    size_t off_cand, off_cnt, off_thr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
+    size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
     size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
     int fb_parts;
     int64_t fb_rows_per_part;
@@ -97,6 +98,37 @@ static void plan_parts(int64_t q_tiles, int64_t n, int tile_rows, int sms, int w
     *rows_per_part = tiles_per_part * tile_rows;
 }
 
+// Filter path: slabs are chosen so that (query tiles x slabs) fills the work units (CTAs or CTA pairs) evenly --
+// thresholds are shared across the slabs of a query (FilterArgs::gthr), so extra slabs cost little.
+static void plan_parts_filter(int64_t q_tiles, int64_t n, int tile_rows, int units, int* parts, int64_t* rows_per_part) {
+    const int64_t c_tiles = ceil_div64(n, tile_rows);
+    int64_t max_p = c_tiles / 64;  // keep >= 64 corpus tiles per slab
+    if (max_p < 1) max_p = 1;
+    if (max_p > 64) max_p = 64;
+    int64_t best_p = 1;
+    double best_waste = 1e30;
+    for (int64_t p = 1; p <= max_p; ++p) {
+        const int64_t items = q_tiles * p;
+        const int64_t rounds = ceil_div64(items, units);
+        const double waste = static_cast<double>(rounds * units) / static_cast<double>(items) - 1.0;
+        if (waste < best_waste - 0.015) {  // prefer fewer slabs unless the gain is > 1.5 %
+            best_waste = waste;
+            best_p = p;
+        }
+    }
+    // tiny corpora / many idle units: fall back to spreading over the units
+    if (q_tiles * best_p < units && c_tiles > best_p) {
+        int64_t p = units / q_tiles;
+        if (p > c_tiles) p = c_tiles;
+        if (p > 1024) p = 1024;
+        if (p > best_p) best_p = p;
+    }
+    const int64_t tiles_per_part = ceil_div64(c_tiles, best_p);
+    best_p = ceil_div64(c_tiles, tiles_per_part);
+    *parts = static_cast<int>(best_p);
+    *rows_per_part = tiles_per_part * tile_rows;
+}
+
 static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p, const DeviceInfo& di,
                      Plan* pl) {
     memset(pl, 0, sizeof *pl);
@@ -125,14 +157,18 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
-        pl->tile_q = tc::kBlockM;
-        pl->q_tiles = ceil_div64(q, tc::kBlockM);
-        plan_parts(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), sms, 1, &pl->parts, &pl->rows_per_part);
+        pl->ncta = ((p->reserved & 1) || sms < 2) ? 1 : 2;  // reserved bit 0: force the single-CTA form (tests / A-B runs)
+        pl->tile_q = tc::kBlockM * pl->ncta;
+        pl->q_tiles = ceil_div64(q, pl->tile_q);
+        int units = sms / pl->ncta;
+        if (units < 1) units = 1;
+        plan_parts_filter(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), units, &pl->parts, &pl->rows_per_part);
     }
     const int64_t q_pad = pl->q_tiles * pl->tile_q;
     pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->parts * kCandCap);
     pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->parts);
     pl->off_thr = carve(sizeof(float) * q_pad * pl->parts);
+    pl->off_gthr = carve(sizeof(uint32_t) * q_pad);
     pl->off_sel = carve(sizeof(uint64_t) * q * pl->R);
     pl->off_bound = carve(sizeof(float) * q);
     pl->off_qerr = carve(sizeof(float) * q_pad);
@@ -208,9 +244,22 @@ int radar_set_device(int device) {
     return RADAR_OK;
 }
 
-int radar_set_profile_events(void* ev_start, void* ev_stop) {
-    g_prof_start = static_cast<cudaEvent_t>(ev_start);
-    g_prof_stop = static_cast<cudaEvent_t>(ev_stop);
+int radar_profile_enable(int enable) {
+    if (enable && !g_prof_start) {
+        RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_start));
+        RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_stop));
+    } else if (!enable && g_prof_start) {
+        cudaEventDestroy(g_prof_start);
+        cudaEventDestroy(g_prof_stop);
+        g_prof_start = g_prof_stop = nullptr;
+    }
+    return RADAR_OK;
+}
+
+int radar_profile_kernel_ms(float* ms_out) {
+    RADAR_ARG_CHECK(ms_out && g_prof_start, "profile_kernel_ms: profiling is not enabled");
+    RADAR_CUDA_CHECK(cudaEventSynchronize(g_prof_stop));
+    RADAR_CUDA_CHECK(cudaEventElapsedTime(ms_out, g_prof_start, g_prof_stop));
     return RADAR_OK;
 }
 
@@ -329,8 +378,9 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(uint32_t) * 4, st));
         tc::FilterLaunch fl{};
         fl.corpus = corpus; fl.queries = queries; fl.mode = params->mode; fl.alpha = alpha; fl.oma = oma;
-        fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part; fl.kp = pl.kp;
-        fl.cand = cand; fl.cnt = cnt; fl.thr = thr; fl.qerr = qerr;
+        fl.q = q; fl.q_tiles = pl.q_tiles; fl.ncta = pl.ncta; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
+        fl.kp = pl.kp; fl.cand = cand; fl.cnt = cnt; fl.thr = thr; fl.qerr = qerr;
+        fl.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
         fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
         fl.num_sms = params->num_sms > 0 ? params->num_sms : di.sms;
         fl.dbg_scores = nullptr;
@@ -426,7 +476,8 @@ int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t*
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     tc::FilterLaunch fl{};
     fl.corpus = corpus; fl.queries = queries; fl.mode = p2.mode; fl.alpha = p2.alpha; fl.oma = 1.0f - p2.alpha;
-    fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part; fl.kp = pl.kp;
+    fl.q = q; fl.q_tiles = pl.q_tiles; fl.ncta = pl.ncta; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
+    fl.kp = pl.kp; fl.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
     fl.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
     fl.cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
     fl.thr = reinterpret_cast<float*>(ws + pl.off_thr);

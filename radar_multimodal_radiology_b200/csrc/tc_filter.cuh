@@ -32,7 +32,8 @@ namespace tc {
 constexpr int kBlockM = 128;          // query rows per tile == TMEM lanes
 constexpr int kFallbackMaxQ = 4096;   // uncertified queries re-run per exact pass
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int kStages = 8;            // shared-memory ring slots
+constexpr int kStages = 8;            // shared-memory ring slots (single-CTA form)
+constexpr int kStagesPair = 12;       // ring slots of the CTA-pair form (half-size stages)
 constexpr int kStageBytes = 16384;    // 128 rows x 128 B
 constexpr int kTmemCols = 512;
 constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
@@ -50,8 +51,10 @@ __host__ __device__ inline int a_cols_for(int mode, int d) {
     return (mode != RADAR_MODE_KL ? d : 0) + (mode != RADAR_MODE_DPR ? 2 * kObsPad : 0);
 }
 
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + static_cast<size_t>(kStages) * kStageBytes +
-                              4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ + 256 /*barriers*/;
+constexpr size_t smem_bytes_for(int ncta) {
+    return 1024 /*align slack*/ + static_cast<size_t>(ncta == 2 ? kStagesPair : kStages) * (kStageBytes / ncta) +
+           4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ + 512 /*barriers*/;
+}
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -85,6 +88,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             __trap();
         }
     }
+}
+// one lane of a converged warp (the operands of the predicated tcgen05 / TMA instruction then stay warp-uniform,
+// so the compiler keeps them in uniform registers instead of emitting an R2UR waterfall loop per instruction)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
@@ -244,151 +258,271 @@ struct FilterArgs {
     const uint16_t* apack;
     const float* qshift;
     int64_t q;          // real queries
-    int64_t q_tiles;
+    int64_t q_tiles;    // work tiles of NCTA * 128 query rows
     int64_t n;          // corpus rows
     int d;
     int parts;
     int64_t rows_per_part;  // multiple of BLOCK_N
     int kp;
-    uint64_t* cand;  // [q_pad][parts][kCandCap]
-    uint32_t* cnt;   // [q_pad][parts]
-    float* thr;      // [q_pad][parts]  final thresholds
+    uint64_t* cand;     // [q_pad][parts][kCandCap]
+    uint32_t* cnt;      // [q_pad][parts]
+    float* thr;         // [q_pad][parts]  final thresholds
+    uint32_t* gthr;     // [q_pad] best published threshold per query (ord-encoded, 0 = none): slabs of the same
+                        // query tile that run later start from it instead of -inf
     float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
 };
 
-template <int MODE>
+// cluster helpers (CTA pairs)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA
+// arrive on the barrier at the same offset in the pair's leader (even) CTA; for the leader itself this is local
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's barrier (both CTAs of a pair call it)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+// M = 256 across the CTA pair: each CTA supplies its own 128 A rows (TMEM) and half of the B rows (smem)
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
+        : "memory");
+}
+
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// NCTA = 1: one CTA per work tile (M = 128).  NCTA = 2: a CTA pair (cluster of 2) per work tile, M = 256 via
+// tcgen05 cta_group::2 -- each CTA streams only half of every corpus tile, which halves both the L2->SM and the
+// shared-memory traffic per MAC (the single-CTA form needs 128 B/clk/SM of smem bandwidth: TMA write + MMA read).
+template <int MODE, int NCTA>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_constant__ CUtensorMap map_kl,
                  const FilterArgs a) {
     constexpr bool HAS_IP = MODE != RADAR_MODE_KL;
     constexpr bool HAS_KL = MODE != RADAR_MODE_DPR;
-    constexpr int BLOCK_N = block_n_for_mode(MODE);
+    constexpr bool PAIR = NCTA == 2;
+    constexpr int BLOCK_N = block_n_for_mode(MODE);     // corpus rows per MMA tile (whole pair)
+    constexpr int LOAD_N = BLOCK_N / NCTA;              // corpus rows this CTA stages per tile
     constexpr int ACC_STAGES = acc_stages_for_mode(MODE);
     constexpr int ACC_COL0 = acc_col0_for_mode(MODE);
     constexpr int A_KL_COL = a_kl_col_for_mode(MODE);
-    constexpr uint32_t IDESC = make_idesc(BLOCK_N);
-    constexpr uint32_t IP_BYTES = BLOCK_N * 128, KL_BYTES = BLOCK_N * 64;
+    constexpr uint32_t IDESC = make_idesc_mn(kBlockM * NCTA, BLOCK_N);
+    constexpr uint32_t IP_BYTES = LOAD_N * 128, KL_BYTES = LOAD_N * 64;
+    constexpr int STAGE_BYTES = kStageBytes / NCTA;
+    constexpr int STAGES = PAIR ? kStagesPair : kStages;
     static_assert(ACC_COL0 + ACC_STAGES * BLOCK_N <= kTmemCols, "TMEM budget");
+    static_assert(LOAD_N % 8 == 0 && IP_BYTES <= STAGE_BYTES, "stage layout");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* stage_base = smem;
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* bars = scratch + 4 * kCandCap;
-    uint64_t* full_bar = bars;                       // [kStages]
-    uint64_t* empty_bar = bars + kStages;            // [kStages]
-    uint64_t* tfull_bar = bars + 2 * kStages;        // [ACC_STAGES]
-    uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]
-    uint64_t* aready_bar = tempty_bar + ACC_STAGES;  // [1]
+    uint64_t* full_bar = bars;                       // [STAGES]      (pair: only the leader's are waited on)
+    uint64_t* empty_bar = bars + STAGES;             // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
+    uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]  (pair: leader's, 8 arrivals)
+    uint64_t* aready_bar = tempty_bar + ACC_STAGES;  // [1]           (pair: leader's, 8 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const int64_t unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;        // work-tile processor id
+    const int64_t units = PAIR ? (gridDim.x >> 1) : gridDim.x;
     const int kblocks = HAS_IP ? a.d / 64 : 0;
     const int64_t items = a.q_tiles * a.parts;
 
     if (warp == 0 && lane == 0) {
         if (HAS_IP) prefetch_tmap(&map_emb);
         if (HAS_KL) prefetch_tmap(&map_kl);
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);
+            mbar_init(&tempty_bar[i], 4 * NCTA);
         }
-        mbar_init(aready_bar, 4);
+        mbar_init(aready_bar, 4 * NCTA);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot);
+    if (warp == 1) {
+        if (PAIR) tmem_alloc_pair(tmem_slot);
+        else tmem_alloc(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) {  // all 512 columns are allocated, so the base is (lane 0, column 0); the MMA issuer relies on it
+        if (threadIdx.x == 0) printf("radar tc_filter: unexpected TMEM base %u\n", tmem_base);
+        __trap();
+    }
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (lane == 0) {
+        // ================================ TMA producer (every CTA: its share of each corpus tile) =================
+        // the whole warp runs the loop converged; one elected lane arms the barrier and issues the copy
+        {
             uint32_t it = 0;
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+            for (int64_t item = unit; item < items; item += units) {
                 const int part = static_cast<int>(item / a.q_tiles);
                 const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
                 const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
                 for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
+                    const int my_row = static_cast<int>(row0) + static_cast<int>(cta_rank) * LOAD_N;
                     for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(&empty_bar[s], ph ^ 1);
-                        mbar_expect_tx(&full_bar[s], IP_BYTES);
-                        tma_load_2d(&map_emb, &full_bar[s], stage_base + s * kStageBytes, kb * 64,
-                                    static_cast<int>(row0));
+                        if (elect_one()) {
+                            if (PAIR) {
+                                if (leader) mbar_expect_tx(&full_bar[s], IP_BYTES * 2);  // both halves land on the leader
+                                tma_load_2d_pair(&map_emb, &full_bar[s], stage_base + s * STAGE_BYTES, kb * 64, my_row);
+                            } else {
+                                mbar_expect_tx(&full_bar[s], IP_BYTES);
+                                tma_load_2d(&map_emb, &full_bar[s], stage_base + s * STAGE_BYTES, kb * 64, my_row);
+                            }
+                        }
+                        __syncwarp();
                     }
                     if (HAS_KL) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(&empty_bar[s], ph ^ 1);
-                        mbar_expect_tx(&full_bar[s], KL_BYTES);
-                        tma_load_2d(&map_kl, &full_bar[s], stage_base + s * kStageBytes, 0, static_cast<int>(row0));
+                        if (elect_one()) {
+                            if (PAIR) {
+                                if (leader) mbar_expect_tx(&full_bar[s], KL_BYTES * 2);
+                                tma_load_2d_pair(&map_kl, &full_bar[s], stage_base + s * STAGE_BYTES, 0, my_row);
+                            } else {
+                                mbar_expect_tx(&full_bar[s], KL_BYTES);
+                                tma_load_2d(&map_kl, &full_bar[s], stage_base + s * STAGE_BYTES, 0, my_row);
+                            }
+                        }
+                        __syncwarp();
                         ++it;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
+        // ================================ MMA issuer (leader CTA only) ================================
+        // converged warp; the tcgen05.mma / tcgen05.commit instructions are issued by one elected lane
+        if (leader) {
             uint32_t it = 0, tile = 0, item_no = 0;
-            for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
+            for (int64_t item = unit; item < items; item += units, ++item_no) {
                 const int part = static_cast<int>(item / a.q_tiles);
                 const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
                 const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
-                mbar_wait(aready_bar, item_no & 1);  // this item's query tile is in TMEM
+                mbar_wait(aready_bar, item_no & 1);  // this item's query tile is in TMEM (both CTAs)
                 tc_fence_after();
                 for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++tile) {
                     const uint32_t as = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
-                    mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogue drained this accumulator
+                    mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogues drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + ACC_COL0 + as * BLOCK_N;
+                    const uint32_t d_tmem = ACC_COL0 + as * BLOCK_N;  // TMEM base is 0: the CTA owns all 512 columns
                     uint32_t acc = 0;
                     for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * kStageBytes), 1024, 2);
+                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * STAGE_BYTES), 1024, 2);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 16) per 64-wide block; +32 B per step
-                            umma_ts(d_tmem, tmem_base + kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, acc);
-                            acc = 1;
+                            for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 16) per 64-wide block; +32 B per step
+                                if (PAIR) umma_ts_pair(d_tmem, kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, (kb | ks) ? 1u : acc);
+                                else umma_ts(d_tmem, kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, (kb | ks) ? 1u : acc);
+                            }
+                            if (PAIR) umma_commit_pair(&empty_bar[s]);  // slot reusable in both CTAs
+                            else umma_commit(&empty_bar[s]);
                         }
-                        umma_commit(&empty_bar[s]);  // slot reusable once these MMAs have read it
+                        __syncwarp();
+                        acc = 1;
                     }
                     if (HAS_KL) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
                         mbar_wait(&full_bar[s], ph);
                         tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * kStageBytes), 512, 4);
-                        const uint32_t a_hi = tmem_base + A_KL_COL, a_lo = a_hi + 8;
-                        umma_ts(d_tmem, a_hi, bdesc, IDESC, acc);      // v_hi . L_hi
-                        umma_ts(d_tmem, a_hi, bdesc + 2, IDESC, 1);    // v_hi . L_lo
-                        umma_ts(d_tmem, a_lo, bdesc, IDESC, 1);        // v_lo . L_hi
-                        umma_ts(d_tmem, a_lo, bdesc + 2, IDESC, 1);    // v_lo . L_lo
-                        umma_commit(&empty_bar[s]);
+                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * STAGE_BYTES), 512, 4);
+                        const uint32_t a_hi = A_KL_COL, a_lo = a_hi + 8;
+                        if (elect_one()) {
+                            if (PAIR) {
+                                umma_ts_pair(d_tmem, a_hi, bdesc, IDESC, acc);      // v_hi . L_hi
+                                umma_ts_pair(d_tmem, a_hi, bdesc + 2, IDESC, 1);    // v_hi . L_lo
+                                umma_ts_pair(d_tmem, a_lo, bdesc, IDESC, 1);        // v_lo . L_hi
+                                umma_ts_pair(d_tmem, a_lo, bdesc + 2, IDESC, 1);    // v_lo . L_lo
+                                umma_commit_pair(&empty_bar[s]);
+                                umma_commit_pair(&tfull_bar[as]);
+                            } else {
+                                umma_ts(d_tmem, a_hi, bdesc, IDESC, acc);
+                                umma_ts(d_tmem, a_hi, bdesc + 2, IDESC, 1);
+                                umma_ts(d_tmem, a_lo, bdesc, IDESC, 1);
+                                umma_ts(d_tmem, a_lo, bdesc + 2, IDESC, 1);
+                                umma_commit(&empty_bar[s]);
+                                umma_commit(&tfull_bar[as]);
+                            }
+                        }
+                        __syncwarp();
                         ++it;
+                    } else {
+                        if (elect_one()) {
+                            if (PAIR) umma_commit_pair(&tfull_bar[as]);  // accumulator complete (both CTAs)
+                            else umma_commit(&tfull_bar[as]);
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&tfull_bar[as]);  // accumulator complete
                 }
             }
         }
     } else {
         // ================================ epilogue warps (2..5) ================================
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        const int r_in_tile = quad * 32 + lane;
+        const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         uint64_t* my_scratch = scratch + (warp - 2) * kCandCap;
         const int a_cols = a_cols_for(MODE, a.d);  // bf16 per packed row
-        uint32_t tile = 0, item_no = 0;
-        for (int64_t item = blockIdx.x; item < items; item += gridDim.x, ++item_no) {
+        uint32_t tile = 0;
+        for (int64_t item = unit; item < items; item += units) {
             const int64_t qtile = item % a.q_tiles;
             const int part = static_cast<int>(item / a.q_tiles);
-            const int64_t qrow = qtile * kBlockM + r_in_tile;
+            const int64_t qrow = qtile * (kBlockM * NCTA) + r_in_tile;
             const bool valid = qrow < a.q;
             const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
             const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
@@ -413,11 +547,17 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(aready_bar);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_leader(aready_bar);
+                    else mbar_arrive(aready_bar);
+                }
             }
             const float shift = a.qshift[qrow];
-            float thr = -CUDART_INF_F;                                    // in canonical-key units
-            float thr_cmp = valid ? -CUDART_INF_F : CUDART_INF_F;         // in accumulator units
+            // start from the best threshold an earlier slab of this query published (a lower bound on the k'-th best
+            // key over the whole corpus, so dropping below it is always safe)
+            const uint32_t g0 = a.parts > 1 ? *reinterpret_cast<volatile const uint32_t*>(a.gthr + qrow) : 0u;
+            float thr = g0 ? ord2f(g0) : -CUDART_INF_F;                    // in canonical-key units
+            float thr_cmp = valid ? (g0 ? __fadd_rn(thr, shift) : -CUDART_INF_F) : CUDART_INF_F;  // accumulator units
             int cnt = 0;
             uint64_t* buf = a.cand + (qrow * a.parts + part) * kCandCap;
 
@@ -473,15 +613,23 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) {
+                    if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+                    else mbar_arrive(&tempty_bar[as]);
+                }
             }
             a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
             a.thr[qrow * a.parts + part] = thr;
+            if (a.parts > 1 && valid && thr > -CUDART_INF_F) atomicMax(a.gthr + qrow, f2ord(thr));
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base);
+    if (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) {
+        if (PAIR) tmem_dealloc_pair(tmem_base);
+        else tmem_dealloc(tmem_base);
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -530,13 +678,15 @@ struct FilterLaunch {
     const radar_queries_t* queries;
     int mode;
     float alpha, oma;
-    int64_t q, q_tiles;
+    int64_t q, q_tiles;   // q_tiles = work tiles of ncta*128 rows
+    int ncta;             // 1 or 2 (CTA pairs)
     int parts;
     int64_t rows_per_part;
     int kp;
     uint64_t* cand;
     uint32_t* cnt;
     float* thr;
+    uint32_t* gthr;   // [q_pad]
     float* qerr;      // [q_pad]
     uint16_t* apack;  // [q_pad][a_cols] followed by qshift [q_pad] floats
     int num_sms;
@@ -544,34 +694,49 @@ struct FilterLaunch {
     cudaEvent_t ev_start, ev_stop;  // optional: recorded around the filter kernel only
 };
 
-template <int MODE>
+template <int MODE, int NCTA>
 static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cudaStream_t st) {
     constexpr int BLOCK_N = block_n_for_mode(MODE);
+    constexpr int LOAD_N = BLOCK_N / NCTA;
     CUtensorMap map_emb, map_kl;
     memset(&map_emb, 0, sizeof map_emb);
     memset(&map_kl, 0, sizeof map_kl);
     int rc;
     if (MODE != RADAR_MODE_KL) {
-        rc = encode_2d_bf16(&map_emb, fl.corpus->emb_bf16, fl.corpus->d, fl.corpus->n, 64, BLOCK_N,
+        rc = encode_2d_bf16(&map_emb, fl.corpus->emb_bf16, fl.corpus->d, fl.corpus->n, 64, LOAD_N,
                             CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     if (MODE != RADAR_MODE_DPR) {
-        rc = encode_2d_bf16(&map_kl, fl.corpus->klpack, RADAR_KLPACK, fl.corpus->n, RADAR_KLPACK, BLOCK_N,
+        rc = encode_2d_bf16(&map_kl, fl.corpus->klpack, RADAR_KLPACK, fl.corpus->n, RADAR_KLPACK, LOAD_N,
                             CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[MODE]) {
-        RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(kSmemBytes)));
-        attr_set[MODE] = true;
+    constexpr size_t smem = smem_bytes_for(NCTA);
+    static bool attr_set = false;
+    if (!attr_set) {
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(smem)));
+        attr_set = true;
     }
     const int64_t items = fl.q_tiles * fl.parts;
-    const int grid = static_cast<int>(items < fl.num_sms ? items : fl.num_sms);
+    int64_t units = fl.num_sms / NCTA;
+    if (units < 1) units = 1;
+    if (units > items) units = items;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(units * NCTA));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (fl.ev_start) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_start, st));
-    tc_filter_kernel<MODE><<<grid, kThreads, kSmemBytes, st>>>(map_emb, map_kl, fa);
-    RADAR_CUDA_CHECK(cudaGetLastError());
+    RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_filter_kernel<MODE, NCTA>, map_emb, map_kl, fa));
     if (fl.ev_stop) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_stop, st));
     return RADAR_OK;
 }
@@ -584,7 +749,7 @@ static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
 }
 
 static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches) {
-    const int64_t q_pad = fl.q_tiles * kBlockM;
+    const int64_t q_pad = fl.q_tiles * kBlockM * fl.ncta;
     const int cols = a_cols_for(fl.mode, fl.corpus->d);
     size_t shift_off = (sizeof(uint16_t) * static_cast<size_t>(q_pad) * cols + 255) / 256 * 256;
     float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fl.apack) + shift_off);
@@ -595,14 +760,21 @@ static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches)
     pa.apack = fl.apack; pa.qshift = qshift; pa.qerr = fl.qerr;
     query_pack_kernel<<<static_cast<unsigned>((q_pad * 32 + 255) / 256), 256, 0, st>>>(pa);
     RADAR_CUDA_CHECK(cudaGetLastError());
+    if (fl.parts > 1) RADAR_CUDA_CHECK(cudaMemsetAsync(fl.gthr, 0, sizeof(uint32_t) * q_pad, st));
     FilterArgs fa{};
     fa.apack = fl.apack; fa.qshift = qshift; fa.q = fl.q; fa.q_tiles = fl.q_tiles; fa.n = fl.corpus->n;
     fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
-    fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.dbg_scores = fl.dbg_scores;
+    fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.gthr = fl.gthr; fa.dbg_scores = fl.dbg_scores;
     int rc;
-    if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR>(fl, fa, st);
-    else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL>(fl, fa, st);
-    else rc = launch_filter_mode<RADAR_MODE_HYBRID>(fl, fa, st);
+    if (fl.ncta == 2) {
+        if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR, 2>(fl, fa, st);
+        else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 2>(fl, fa, st);
+        else rc = launch_filter_mode<RADAR_MODE_HYBRID, 2>(fl, fa, st);
+    } else {
+        if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR, 1>(fl, fa, st);
+        else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 1>(fl, fa, st);
+        else rc = launch_filter_mode<RADAR_MODE_HYBRID, 1>(fl, fa, st);
+    }
     if (rc) return rc;
     *launches = 2;
     return RADAR_OK;
