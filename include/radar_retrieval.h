@@ -102,7 +102,7 @@ typedef struct radar_search_params {
     float alpha;       /* hybrid weight (RetrievalConfig.hybrid_alpha, dpr.py:187); ignored unless HYBRID */
     int32_t overfetch; /* candidates re-scored per query on the filter path; 0 = automatic */
     int32_t num_sms;   /* 0 = all SMs of the device (tests use small values to force multi-part merges) */
-    int32_t reserved;  /* flags; bit 0: tensor-core filter uses single CTAs instead of cta_group::2 pairs */
+    int32_t reserved;  /* must be 0 */
 } radar_search_params_t;
 
 /* Per-call statistics written to HOST memory when the pointer is non-NULL (forces a stream sync). */

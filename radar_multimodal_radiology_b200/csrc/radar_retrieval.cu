@@ -56,8 +56,8 @@ struct Plan {
     int kp;            // candidates a compaction keeps (k on the exact path, k' on the filter path)
     int R;             // candidates selected per query for re-scoring (= kp)
     int64_t q_tiles;   // query tiles of the main pass
-    int tile_q;        // rows per query tile (64 scan / 128 or 256 filter)
-    int ncta;          // CTAs per filter work tile (2 = cta_group::2 pairs)
+    int tile_q;        // rows per query tile (64 scan / 256 filter)
+    int units;         // CTA pairs the filter launches
     int parts;
     int64_t rows_per_part;
     // workspace offsets (bytes)
@@ -157,18 +157,19 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
-        pl->ncta = ((p->reserved & 1) || sms < 2) ? 1 : 2;  // reserved bit 0: force the single-CTA form (tests / A-B runs)
-        pl->tile_q = tc::kBlockM * pl->ncta;
+        pl->tile_q = tc::kTileQ;
         pl->q_tiles = ceil_div64(q, pl->tile_q);
-        int units = sms / pl->ncta;
+        int units = sms / 2;  // one CTA pair (tcgen05 cta_group::2) per two SMs
         if (units < 1) units = 1;
+        if (units > tc::kMaxUnits) units = tc::kMaxUnits;
+        pl->units = units;
         plan_parts_filter(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), units, &pl->parts, &pl->rows_per_part);
     }
     const int64_t q_pad = pl->q_tiles * pl->tile_q;
     pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->parts * kCandCap);
     pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->parts);
     pl->off_thr = carve(sizeof(float) * q_pad * pl->parts);
-    pl->off_gthr = carve(sizeof(uint32_t) * q_pad);
+    pl->off_gthr = carve(tc::gthr_region_bytes(q_pad));
     pl->off_sel = carve(sizeof(uint64_t) * q * pl->R);
     pl->off_bound = carve(sizeof(float) * q);
     pl->off_qerr = carve(sizeof(float) * q_pad);
@@ -378,11 +379,11 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(uint32_t) * 4, st));
         tc::FilterLaunch fl{};
         fl.corpus = corpus; fl.queries = queries; fl.mode = params->mode; fl.alpha = alpha; fl.oma = oma;
-        fl.q = q; fl.q_tiles = pl.q_tiles; fl.ncta = pl.ncta; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
+        fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
         fl.kp = pl.kp; fl.cand = cand; fl.cnt = cnt; fl.thr = thr; fl.qerr = qerr;
         fl.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
         fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
-        fl.num_sms = params->num_sms > 0 ? params->num_sms : di.sms;
+        fl.units = pl.units; fl.device_sms = di.sms;
         fl.dbg_scores = nullptr;
         fl.ev_start = g_prof_start; fl.ev_stop = g_prof_stop;
         int nl = 0;
@@ -476,14 +477,14 @@ int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t*
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     tc::FilterLaunch fl{};
     fl.corpus = corpus; fl.queries = queries; fl.mode = p2.mode; fl.alpha = p2.alpha; fl.oma = 1.0f - p2.alpha;
-    fl.q = q; fl.q_tiles = pl.q_tiles; fl.ncta = pl.ncta; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
+    fl.q = q; fl.q_tiles = pl.q_tiles; fl.parts = pl.parts; fl.rows_per_part = pl.rows_per_part;
     fl.kp = pl.kp; fl.gthr = reinterpret_cast<uint32_t*>(ws + pl.off_gthr);
     fl.cand = reinterpret_cast<uint64_t*>(ws + pl.off_cand);
     fl.cnt = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
     fl.thr = reinterpret_cast<float*>(ws + pl.off_thr);
     fl.qerr = reinterpret_cast<float*>(ws + pl.off_qerr);
     fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
-    fl.num_sms = p2.num_sms > 0 ? p2.num_sms : di.sms;
+    fl.units = pl.units; fl.device_sms = di.sms;
     fl.dbg_scores = out_keys;
     int nl = 0;
     return tc::launch_filter(fl, static_cast<cudaStream_t>(stream), &nl);

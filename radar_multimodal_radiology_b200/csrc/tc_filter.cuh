@@ -1,27 +1,34 @@
 // tc_filter.cuh -- tcgen05 (5th-gen tensor core) filter kernel for sm_100a.
 //
-// One CTA per SM, persistent over work items (query tile of 128 rows, corpus slab).
+// One CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 256) per two SMs, persistent over work items
+// (query tile of 256 rows, corpus slab).
 //   * the QUERY tile is the A operand and lives in TENSOR MEMORY for the whole slab sweep
 //     (bf16 pairs packed in 32-bit TMEM columns, written once per item with tcgen05.st) -- shared
 //     memory holds nothing but the streamed corpus tiles;
-//   * CORPUS tiles are the B operand: TMA (cp.async.bulk.tensor.2d, 128B/64B swizzle) streams
-//     BLOCK_N x 64 bf16 K-blocks of the embedding matrix (and one BLOCK_N x 32 block of the
-//     [log q hi | log q lo] pack) through an mbarrier ring of kStages shared-memory slots;
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (A from TMEM, B from smem
-//     descriptors) into one of kAccStages fp32 accumulators in TMEM;
-//   * four epilogue warps read the accumulator back with tcgen05.ld (one query row per thread),
+//   * CORPUS tiles are the B operand: TMA (cp.async.bulk.tensor.2d, 128B/64B swizzle) streams each CTA's
+//     half (BLOCK_N/2 rows) of every tile -- d/64 K-blocks of the embedding matrix plus one block of the
+//     [log q hi | log q lo] pack -- into a ring of TILE-ALIGNED shared-memory slots, so that every
+//     shared-memory matrix descriptor is "slot base + compile-time constant" and the issue loop is
+//     straight-line code (one mbarrier wait per two K-blocks);
+//   * one elected thread of the leader CTA issues tcgen05.mma.cta_group::2.kind::f16 (A from TMEM, B from
+//     smem descriptors) into one of ACC_STAGES fp32 accumulators in TMEM;
+//   * four epilogue warps per CTA read the accumulator back with tcgen05.ld (one query row per thread),
 //     compare against the row's running threshold and append survivors to the row's candidate buffer
-//     in global memory -- the Q x N score matrix never exists outside TMEM.
+//     in global memory -- the Q x N score matrix never exists outside TMEM;
+//   * pairs that sweep the same slab keep within `window` tiles of each other (a progress word per pair,
+//     polled by the TMA producer), so a corpus tile is fetched from HBM once and then served from L2 to
+//     every query tile instead of once per query tile.
 //
 // Filter value for (query i, case n):
 //     DPR    f = sum_t bf16(e_q[t]) bf16(e_c[t])
-//     KL     f = sum_j (p_hi+p_lo)[j] (L_hi+L_lo)[n][j]                  (all four hi/lo products)
-//     hybrid f = sum_t bf16(alpha e_q[t]) bf16(e_c[t]) + sum_j (v_hi+v_lo)[j] (L_hi+L_lo)[n][j],  v = (1-alpha) p
+//     KL     f = sum_j (p_hi L_hi + p_hi L_lo + p_lo L_hi)[j]                     (lo*lo dropped: < 2^-18 |p||L|)
+//     hybrid f = sum_t bf16(alpha e_q[t]) bf16(e_c[t]) + sum_j (v_hi L_hi + v_hi L_lo + v_lo L_hi)[j],  v = (1-alpha) p
 // and the ranking key handed to the candidate buffer is f - shift_i, shift = H (KL) / (1-alpha) H (hybrid),
 // i.e. it approximates the canonical key of common.cuh within qerr_i (see query_pack_kernel).
 #pragma once
 #include <cuda.h>
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "scan_kernels.cuh"
@@ -29,16 +36,19 @@
 namespace radar {
 namespace tc {
 
-constexpr int kBlockM = 128;          // query rows per tile == TMEM lanes
+constexpr int kBlockM = 128;          // query rows per CTA == TMEM lanes
+constexpr int kTileQ = 2 * kBlockM;   // query rows per work tile (CTA pair)
 constexpr int kFallbackMaxQ = 4096;   // uncertified queries re-run per exact pass
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int kStages = 8;            // shared-memory ring slots (single-CTA form)
-constexpr int kStagesPair = 12;       // ring slots of the CTA-pair form (half-size stages)
-constexpr int kStageBytes = 16384;    // 128 rows x 128 B
 constexpr int kTmemCols = 512;
 constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
-constexpr int kAKlCols = 16;          // [p_hi (8 cols) | p_lo (8 cols)]
+constexpr int kRingBytes = 192 * 1024;  // shared-memory ring of tile slots (per CTA)
+constexpr int kMaxSlots = 8;
+constexpr int kMaxGroups = 4;         // full barriers per slot: one per two K-blocks
+constexpr int kMaxUnits = 1024;       // CTA pairs a launch may use (progress words in the workspace)
+constexpr int kProgressEvery = 8;     // tiles between progress publications / window checks
 constexpr uint32_t kSpinLimit = 1u << 27;
+constexpr uint32_t kWindowSpinLimit = 1u << 16;  // polls (x ~1 us) before a pair stops honouring the window
 
 __host__ __device__ constexpr int block_n_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? 112 : 128; }
 __host__ __device__ constexpr int acc_stages_for_mode(int mode) { return mode == RADAR_MODE_KL ? 3 : 2; }
@@ -50,11 +60,20 @@ __host__ __device__ constexpr int a_kl_col_for_mode(int mode) { return mode == R
 __host__ __device__ inline int a_cols_for(int mode, int d) {
     return (mode != RADAR_MODE_KL ? d : 0) + (mode != RADAR_MODE_DPR ? 2 * kObsPad : 0);
 }
-
-constexpr size_t smem_bytes_for(int ncta) {
-    return 1024 /*align slack*/ + static_cast<size_t>(ncta == 2 ? kStagesPair : kStages) * (kStageBytes / ncta) +
-           4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ + 512 /*barriers*/;
+// shared-memory geometry of one tile slot (per CTA: BLOCK_N/2 corpus rows)
+__host__ __device__ constexpr int sub_ip_bytes(int mode) { return block_n_for_mode(mode) / 2 * 128; }  // one K-block
+__host__ __device__ constexpr int sub_kl_bytes(int mode) { return block_n_for_mode(mode) / 2 * 64; }
+__host__ __device__ constexpr int slot_stride_for(int mode, int kblocks) {
+    return (kblocks * sub_ip_bytes(mode) + (mode != RADAR_MODE_DPR ? sub_kl_bytes(mode) : 0) + 1023) / 1024 * 1024;
 }
+__host__ __device__ constexpr int slots_for(int mode, int kblocks) {
+    return kRingBytes / slot_stride_for(mode, kblocks) > kMaxSlots ? kMaxSlots
+                                                                  : kRingBytes / slot_stride_for(mode, kblocks);
+}
+__host__ __device__ constexpr int groups_for(int kblocks) { return kblocks <= 1 ? 1 : (kblocks + 1) / 2; }
+
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ +
+                              1024 /*barriers*/;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -102,44 +121,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-            smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// D[tmem] (+)= A[tmem] * B[smem]^T ; kind::f16 with bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on an mbarrier once every MMA issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
 
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
@@ -175,6 +161,8 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
 
 // shared-memory matrix descriptor, K-major operand, swizzled canonical layout
 //   SW128: rows of 128 B, 8-row atoms 1024 B apart (layout type 2);  SW64: rows of 64 B, atoms 512 B apart (type 4)
+// The start-address field is (addr >> 4) in bits [0,14); shared-memory addresses stay below 256 KB, so adding
+// (byte offset >> 4) to a descriptor never carries out of the field.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);        // start address,   bits [0,14)
@@ -185,11 +173,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
     // kind::f16: D=F32 (bits 4-5 = 1), A=BF16 (bits 7-9 = 1), B=BF16 (bits 10-12 = 1), K-major A and B,
     // N>>3 at bits 17-22, M>>4 at bits 24-28
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(kBlockM >> 4) << 24);
+           (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // ---- query pack: fp32 queries -> bf16 A rows + per-query shift / error bound -----------------------------
@@ -242,12 +230,13 @@ __global__ void __launch_bounds__(256) query_pack_kernel(const PackArgs a) {
         float shift = 0.0f;
         if (valid && has_kl) shift = a.mode == RADAR_MODE_HYBRID ? __fmul_rn(a.oma, a.entropy[row]) : a.entropy[row];
         // |canonical key - filter key| <= qerr  (derivation in DESIGN.md, "certificate"):
-        //   bf16 RN of both embedding operands: (2^-8 + 2^-18) |a||c| ; tensor-core fp32 accumulation of <= 576
-        //   exact products and the canonical fp32 chain: <= 2^-13 (|a||c| + sum|v||L|) ; hi/lo split of v and L:
-        //   2^-17 sum|v||L| ; canonical combine / shift roundings: 2^-20 of the magnitudes involved.
+        //   bf16 RN of both embedding operands: (2^-8 + 2^-18) |a||c| ; tensor-core fp32 accumulation of <= 560
+        //   exact products and the canonical fp32 chain: <= 2^-13 (|a||c| + sum|v||L|) ; hi/lo split of v and L
+        //   with the lo*lo product dropped: (2^-17 + 2^-18) sum|v||L| ; canonical combine / shift roundings:
+        //   2^-20 of the magnitudes involved.
         const float ip_mag = sqrtf(ss) * a.emb_max_norm;
         const float kl_mag = sv * a.logq_max_abs;
-        const float e = 0.00403f * ip_mag + 1.6e-4f * kl_mag + 1e-6f * (fabsf(shift) + ip_mag + kl_mag) + 1e-30f;
+        const float e = 0.00403f * ip_mag + 1.65e-4f * kl_mag + 1e-6f * (fabsf(shift) + ip_mag + kl_mag) + 1e-30f;
         a.qshift[row] = shift;
         a.qerr[row] = e;
     }
@@ -258,7 +247,7 @@ struct FilterArgs {
     const uint16_t* apack;
     const float* qshift;
     int64_t q;          // real queries
-    int64_t q_tiles;    // work tiles of NCTA * 128 query rows
+    int64_t q_tiles;    // work tiles of 256 query rows
     int64_t n;          // corpus rows
     int d;
     int parts;
@@ -269,6 +258,8 @@ struct FilterArgs {
     float* thr;         // [q_pad][parts]  final thresholds
     uint32_t* gthr;     // [q_pad] best published threshold per query (ord-encoded, 0 = none): slabs of the same
                         // query tile that run later start from it instead of -inf
+    unsigned long long* progress;  // [units] (round << 32 | tiles loaded) of every pair; zeroed before the launch
+    int window;         // tiles a pair may run ahead of the slowest pair sweeping the same slab (0 = unbounded)
     float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
 };
 
@@ -288,11 +279,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 // TMA load whose completion bytes are credited to the LEADER CTA's barrier (both CTAs of a pair call it)
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint32_t bar_addr, uint32_t dst_addr, int c0,
+                                                 int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
-            "r"(smem_u32(dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+            "r"(dst_addr),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst) {
@@ -304,7 +296,8 @@ __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst) {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
 }
-// M = 256 across the CTA pair: each CTA supplies its own 128 A rows (TMEM) and half of the B rows (smem)
+// D[tmem] (+)= A[tmem] * B[smem]^T ; kind::f16 with bf16 inputs, fp32 accumulate.  M = 256 across the CTA pair:
+// each CTA supplies its own 128 A rows (TMEM) and half of the B rows (smem).
 __device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
     asm volatile(
@@ -314,7 +307,8 @@ __device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, u
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// commit -> arrive on the barrier at this offset in BOTH CTAs of the pair
+// commit -> arrive (once every MMA issued so far by this thread has completed) on the barrier at this offset in
+// BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
     const uint16_t mask = 3;
     asm volatile(
@@ -324,74 +318,74 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         : "memory");
 }
 
-__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
-           (static_cast<uint32_t>(m >> 4) << 24);
+__device__ __forceinline__ unsigned long long ld_progress(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_progress(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// NCTA = 1: one CTA per work tile (M = 128).  NCTA = 2: a CTA pair (cluster of 2) per work tile, M = 256 via
-// tcgen05 cta_group::2 -- each CTA streams only half of every corpus tile, which halves both the L2->SM and the
-// shared-memory traffic per MAC (the single-CTA form needs 128 B/clk/SM of smem bandwidth: TMA write + MMA read).
-template <int MODE, int NCTA>
+// KB_T > 0: the embedding K-block count (d / 64) is a compile-time constant and the issue / load loops unroll
+// completely (KB_T = 8 is BiomedCLIP's d = 512); KB_T = 0: d is read from the arguments.
+template <int MODE, int KB_T>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_constant__ CUtensorMap map_kl,
                  const FilterArgs a) {
     constexpr bool HAS_IP = MODE != RADAR_MODE_KL;
     constexpr bool HAS_KL = MODE != RADAR_MODE_DPR;
-    constexpr bool PAIR = NCTA == 2;
     constexpr int BLOCK_N = block_n_for_mode(MODE);     // corpus rows per MMA tile (whole pair)
-    constexpr int LOAD_N = BLOCK_N / NCTA;              // corpus rows this CTA stages per tile
+    constexpr int LOAD_N = BLOCK_N / 2;                 // corpus rows this CTA stages per tile
     constexpr int ACC_STAGES = acc_stages_for_mode(MODE);
     constexpr int ACC_COL0 = acc_col0_for_mode(MODE);
     constexpr int A_KL_COL = a_kl_col_for_mode(MODE);
-    constexpr uint32_t IDESC = make_idesc_mn(kBlockM * NCTA, BLOCK_N);
-    constexpr uint32_t IP_BYTES = LOAD_N * 128, KL_BYTES = LOAD_N * 64;
-    constexpr int STAGE_BYTES = kStageBytes / NCTA;
-    constexpr int STAGES = PAIR ? kStagesPair : kStages;
+    constexpr uint32_t IDESC = make_idesc_mn(kTileQ, BLOCK_N);
+    constexpr int SUB_IP = sub_ip_bytes(MODE), SUB_KL = sub_kl_bytes(MODE);
     static_assert(ACC_COL0 + ACC_STAGES * BLOCK_N <= kTmemCols, "TMEM budget");
-    static_assert(LOAD_N % 8 == 0 && IP_BYTES <= STAGE_BYTES, "stage layout");
+    static_assert(LOAD_N % 8 == 0 && BLOCK_N % 16 == 0, "tile shape");
+    static_assert(HAS_IP || KB_T == 0, "KL mode has no embedding K-blocks");
+
+    const int kblocks = HAS_IP ? (KB_T > 0 ? KB_T : a.d / 64) : 0;
+    const int groups = groups_for(kblocks);
+    const int slot_stride = slot_stride_for(MODE, kblocks);
+    const int slots = slots_for(MODE, kblocks);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* stage_base = smem;
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kRingBytes);
     uint64_t* bars = scratch + 4 * kCandCap;
-    uint64_t* full_bar = bars;                       // [STAGES]      (pair: only the leader's are waited on)
-    uint64_t* empty_bar = bars + STAGES;             // [STAGES]
-    uint64_t* tfull_bar = bars + 2 * STAGES;         // [ACC_STAGES]
-    uint64_t* tempty_bar = tfull_bar + ACC_STAGES;   // [ACC_STAGES]  (pair: leader's, 8 arrivals)
-    uint64_t* aready_bar = tempty_bar + ACC_STAGES;  // [1]           (pair: leader's, 8 arrivals)
+    uint64_t* full_bar = bars;                                   // [kMaxSlots][kMaxGroups] (only the leader's are waited on)
+    uint64_t* empty_bar = full_bar + kMaxSlots * kMaxGroups;      // [kMaxSlots]
+    uint64_t* tfull_bar = empty_bar + kMaxSlots;                  // [ACC_STAGES]
+    uint64_t* tempty_bar = tfull_bar + 3;                         // [ACC_STAGES]  (leader's, 8 arrivals)
+    uint64_t* aready_bar = tempty_bar + 3;                        // [1]           (leader's, 8 arrivals)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready_bar + 1);
+    const uint32_t ring_addr = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t cta_rank = cluster_ctarank();
     const bool leader = cta_rank == 0;
-    const int64_t unit = PAIR ? (blockIdx.x >> 1) : blockIdx.x;        // work-tile processor id
-    const int64_t units = PAIR ? (gridDim.x >> 1) : gridDim.x;
-    const int kblocks = HAS_IP ? a.d / 64 : 0;
+    const int64_t unit = blockIdx.x >> 1;        // work-tile processor id (CTA pair)
+    const int64_t units = gridDim.x >> 1;
     const int64_t items = a.q_tiles * a.parts;
 
     if (warp == 0 && lane == 0) {
         if (HAS_IP) prefetch_tmap(&map_emb);
         if (HAS_KL) prefetch_tmap(&map_kl);
-        for (int i = 0; i < STAGES; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
-        }
+        for (int i = 0; i < kMaxSlots * kMaxGroups; ++i) mbar_init(&full_bar[i], 1);
+        for (int i = 0; i < kMaxSlots; ++i) mbar_init(&empty_bar[i], 1);
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4 * NCTA);
+            mbar_init(&tempty_bar[i], 8);
         }
-        mbar_init(aready_bar, 4 * NCTA);
+        mbar_init(aready_bar, 8);
         fence_barrier_init();
     }
-    if (warp == 1) {
-        if (PAIR) tmem_alloc_pair(tmem_slot);
-        else tmem_alloc(tmem_slot);
-    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot);
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything is signalled remotely
+    cluster_sync_all();  // the peer's barriers are initialised before anything is signalled remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tmem_base != 0) {  // all 512 columns are allocated, so the base is (lane 0, column 0); the MMA issuer relies on it
@@ -400,113 +394,134 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     }
 
     if (warp == 0) {
-        // ================================ TMA producer (every CTA: its share of each corpus tile) =================
-        // the whole warp runs the loop converged; one elected lane arms the barrier and issues the copy
-        {
-            uint32_t it = 0;
-            for (int64_t item = unit; item < items; item += units) {
-                const int part = static_cast<int>(item / a.q_tiles);
-                const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
-                const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
-                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
+        // ================================ TMA producer (every CTA: its half of each corpus tile) =================
+        // the whole warp runs the loop converged; one elected lane arms the barriers and issues the copies
+        uint32_t slot = 0, sph = 0, round = 0;
+        const bool publish = a.window > 0 && leader;  // progress is published even after this pair stopped waiting
+        bool honour_window = publish;
+        for (int64_t item = unit; item < items; item += units, ++round) {
+            const int part = static_cast<int>(item / a.q_tiles);
+            const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+            const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+            // pairs sweeping the same slab in this round: items [part*q_tiles, (part+1)*q_tiles) of round `round`
+            const int64_t round_base = static_cast<int64_t>(round) * units;
+            const int peer_lo = static_cast<int>(max(static_cast<int64_t>(0), part * a.q_tiles - round_base));
+            const int peer_hi = static_cast<int>(min(min(units, items - round_base), (part + 1) * a.q_tiles - round_base));
+            uint32_t j = 0;
+            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++j) {
+                if (publish && (j % kProgressEvery) == 0) {
+                    const unsigned long long mine = (static_cast<unsigned long long>(round) << 32) | j;
+                    if (lane == 0) st_progress(a.progress + unit, mine);
+                    if (honour_window && j > static_cast<uint32_t>(a.window)) {
+                        const unsigned long long need = mine - static_cast<unsigned long long>(a.window);
+                        uint32_t polls = 0;
+                        while (true) {
+                            unsigned long long m = ~0ull;
+                            for (int u = peer_lo + lane; u < peer_hi; u += 32) m = min(m, ld_progress(a.progress + u));
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                            if (m >= need) break;
+                            if (++polls > kWindowSpinLimit) {  // never a correctness matter: stop waiting for good
+                                honour_window = false;
+                                break;
+                            }
+                            __nanosleep(500);
+                        }
+                    }
+                }
+                mbar_wait(&empty_bar[slot], sph ^ 1);
+                if (elect_one()) {
+                    const uint32_t dst = ring_addr + slot * slot_stride;
+                    const uint32_t fb = smem_u32(&full_bar[slot * kMaxGroups]);
                     const int my_row = static_cast<int>(row0) + static_cast<int>(cta_rank) * LOAD_N;
-                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(&empty_bar[s], ph ^ 1);
-                        if (elect_one()) {
-                            if (PAIR) {
-                                if (leader) mbar_expect_tx(&full_bar[s], IP_BYTES * 2);  // both halves land on the leader
-                                tma_load_2d_pair(&map_emb, &full_bar[s], stage_base + s * STAGE_BYTES, kb * 64, my_row);
-                            } else {
-                                mbar_expect_tx(&full_bar[s], IP_BYTES);
-                                tma_load_2d(&map_emb, &full_bar[s], stage_base + s * STAGE_BYTES, kb * 64, my_row);
+#pragma unroll
+                    for (int g = 0; g < (KB_T > 0 ? groups_for(KB_T) : kMaxGroups); ++g) {
+                        if (g < groups) {
+                            const int kb0 = 2 * g, kb1 = min(kblocks, 2 * g + 2);
+                            const bool last = g == groups - 1;
+                            if (leader) {  // both halves land on the leader's barrier
+                                const uint32_t bytes = (kb1 - kb0) * (LOAD_N * 128) + ((last && HAS_KL) ? LOAD_N * 64 : 0);
+                                mbar_expect_tx(&full_bar[slot * kMaxGroups + g], bytes * 2);
                             }
-                        }
-                        __syncwarp();
-                    }
-                    if (HAS_KL) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(&empty_bar[s], ph ^ 1);
-                        if (elect_one()) {
-                            if (PAIR) {
-                                if (leader) mbar_expect_tx(&full_bar[s], KL_BYTES * 2);
-                                tma_load_2d_pair(&map_kl, &full_bar[s], stage_base + s * STAGE_BYTES, 0, my_row);
-                            } else {
-                                mbar_expect_tx(&full_bar[s], KL_BYTES);
-                                tma_load_2d(&map_kl, &full_bar[s], stage_base + s * STAGE_BYTES, 0, my_row);
+                            if (HAS_IP) {
+#pragma unroll
+                                for (int kk = 0; kk < 2; ++kk) {
+                                    const int kb = kb0 + kk;
+                                    if (kb < kb1) tma_load_2d_pair(&map_emb, fb + g * 8, dst + kb * SUB_IP, kb * 64, my_row);
+                                }
                             }
+                            if (last && HAS_KL) tma_load_2d_pair(&map_kl, fb + g * 8, dst + kblocks * SUB_IP, 0, my_row);
                         }
-                        __syncwarp();
-                        ++it;
                     }
+                }
+                __syncwarp();
+                if (++slot == static_cast<uint32_t>(slots)) {
+                    slot = 0;
+                    sph ^= 1;
                 }
             }
         }
+        if (a.window > 0 && leader && lane == 0) st_progress(a.progress + unit, ~0ull);  // nobody waits for a finished pair
     } else if (warp == 1) {
         // ================================ MMA issuer (leader CTA only) ================================
         // converged warp; the tcgen05.mma / tcgen05.commit instructions are issued by one elected lane
         if (leader) {
-            uint32_t it = 0, tile = 0, item_no = 0;
+            uint32_t slot = 0, sph = 0, as = 0, aph = 0, item_no = 0;
             for (int64_t item = unit; item < items; item += units, ++item_no) {
                 const int part = static_cast<int>(item / a.q_tiles);
                 const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
                 const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
                 mbar_wait(aready_bar, item_no & 1);  // this item's query tile is in TMEM (both CTAs)
                 tc_fence_after();
-                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++tile) {
-                    const uint32_t as = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
+                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
                     mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogues drained this accumulator
                     tc_fence_after();
-                    const uint32_t d_tmem = ACC_COL0 + as * BLOCK_N;  // TMEM base is 0: the CTA owns all 512 columns
-                    uint32_t acc = 0;
-                    for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * STAGE_BYTES), 1024, 2);
-                        if (elect_one()) {
+                    const uint32_t d_tmem = ACC_COL0 + as * BLOCK_N;  // TMEM base is 0: the pair owns all 512 columns
+                    const uint32_t sbase = ring_addr + slot * slot_stride;
+                    const uint64_t desc_ip = make_smem_desc(sbase, 1024, 2);
+                    const uint64_t desc_kl = make_smem_desc(sbase + kblocks * SUB_IP, 512, 4);
+                    uint64_t* fb = &full_bar[slot * kMaxGroups];
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {  // 4 x (K = 16) per 64-wide block; +32 B per step
-                                if (PAIR) umma_ts_pair(d_tmem, kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, (kb | ks) ? 1u : acc);
-                                else umma_ts(d_tmem, kb * 32 + ks * 8, bdesc + static_cast<uint64_t>(ks * 2), IDESC, (kb | ks) ? 1u : acc);
+                    for (int g = 0; g < (KB_T > 0 ? groups_for(KB_T) : kMaxGroups); ++g) {
+                        if (g < groups) {
+                            const bool last = g == groups - 1;
+                            mbar_wait(&fb[g], sph);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                if (HAS_IP) {
+#pragma unroll
+                                    for (int kk = 0; kk < 2; ++kk) {
+                                        const int kb = 2 * g + kk;
+                                        if (kb < kblocks) {
+#pragma unroll
+                                            for (int ks = 0; ks < 4; ++ks)  // 4 x (K = 16) per 64-wide block; +32 B per step
+                                                umma_ts_pair(d_tmem, kb * 32 + ks * 8,
+                                                             desc_ip + static_cast<uint64_t>((kb * SUB_IP + ks * 32) >> 4), IDESC,
+                                                             (kb | ks) ? 1u : 0u);
+                                        }
+                                    }
+                                }
+                                if (last) {
+                                    if (HAS_KL) {
+                                        const uint32_t a_hi = A_KL_COL, a_lo = a_hi + 8;
+                                        umma_ts_pair(d_tmem, a_hi, desc_kl, IDESC, HAS_IP ? 1u : 0u);  // v_hi . L_hi
+                                        umma_ts_pair(d_tmem, a_hi, desc_kl + 2, IDESC, 1u);             // v_hi . L_lo
+                                        umma_ts_pair(d_tmem, a_lo, desc_kl, IDESC, 1u);                 // v_lo . L_hi
+                                    }
+                                    umma_commit_pair(&empty_bar[slot]);  // slot reusable in both CTAs
+                                    umma_commit_pair(&tfull_bar[as]);    // accumulator complete (both CTAs)
+                                }
                             }
-                            if (PAIR) umma_commit_pair(&empty_bar[s]);  // slot reusable in both CTAs
-                            else umma_commit(&empty_bar[s]);
+                            __syncwarp();
                         }
-                        __syncwarp();
-                        acc = 1;
                     }
-                    if (HAS_KL) {
-                        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint64_t bdesc = make_smem_desc(smem_u32(stage_base + s * STAGE_BYTES), 512, 4);
-                        const uint32_t a_hi = A_KL_COL, a_lo = a_hi + 8;
-                        if (elect_one()) {
-                            if (PAIR) {
-                                umma_ts_pair(d_tmem, a_hi, bdesc, IDESC, acc);      // v_hi . L_hi
-                                umma_ts_pair(d_tmem, a_hi, bdesc + 2, IDESC, 1);    // v_hi . L_lo
-                                umma_ts_pair(d_tmem, a_lo, bdesc, IDESC, 1);        // v_lo . L_hi
-                                umma_ts_pair(d_tmem, a_lo, bdesc + 2, IDESC, 1);    // v_lo . L_lo
-                                umma_commit_pair(&empty_bar[s]);
-                                umma_commit_pair(&tfull_bar[as]);
-                            } else {
-                                umma_ts(d_tmem, a_hi, bdesc, IDESC, acc);
-                                umma_ts(d_tmem, a_hi, bdesc + 2, IDESC, 1);
-                                umma_ts(d_tmem, a_lo, bdesc, IDESC, 1);
-                                umma_ts(d_tmem, a_lo, bdesc + 2, IDESC, 1);
-                                umma_commit(&empty_bar[s]);
-                                umma_commit(&tfull_bar[as]);
-                            }
-                        }
-                        __syncwarp();
-                        ++it;
-                    } else {
-                        if (elect_one()) {
-                            if (PAIR) umma_commit_pair(&tfull_bar[as]);  // accumulator complete (both CTAs)
-                            else umma_commit(&tfull_bar[as]);
-                        }
-                        __syncwarp();
+                    if (++slot == static_cast<uint32_t>(slots)) {
+                        slot = 0;
+                        sph ^= 1;
+                    }
+                    if (++as == ACC_STAGES) {
+                        as = 0;
+                        aph ^= 1;
                     }
                 }
             }
@@ -518,11 +533,11 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         uint64_t* my_scratch = scratch + (warp - 2) * kCandCap;
         const int a_cols = a_cols_for(MODE, a.d);  // bf16 per packed row
-        uint32_t tile = 0;
+        uint32_t as = 0, aph = 0;
         for (int64_t item = unit; item < items; item += units) {
             const int64_t qtile = item % a.q_tiles;
             const int part = static_cast<int>(item / a.q_tiles);
-            const int64_t qrow = qtile * (kBlockM * NCTA) + r_in_tile;
+            const int64_t qrow = qtile * kTileQ + r_in_tile;
             const bool valid = qrow < a.q;
             const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
             const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
@@ -547,10 +562,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 tmem_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (PAIR) mbar_arrive_leader(aready_bar);
-                    else mbar_arrive(aready_bar);
-                }
+                if (lane == 0) mbar_arrive_leader(aready_bar);
             }
             const float shift = a.qshift[qrow];
             // start from the best threshold an earlier slab of this query published (a lower bound on the k'-th best
@@ -561,8 +573,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             int cnt = 0;
             uint64_t* buf = a.cand + (qrow * a.parts + part) * kCandCap;
 
-            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++tile) {
-                const uint32_t as = tile % ACC_STAGES, aph = (tile / ACC_STAGES) & 1;
+            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N;
@@ -613,9 +624,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
-                    else mbar_arrive(&tempty_bar[as]);
+                if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aph ^= 1;
                 }
             }
             a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
@@ -625,11 +637,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
-    if (warp == 1) {
-        if (PAIR) tmem_dealloc_pair(tmem_base);
-        else tmem_dealloc(tmem_base);
-    }
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) tmem_dealloc_pair(tmem_base);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -678,26 +687,30 @@ struct FilterLaunch {
     const radar_queries_t* queries;
     int mode;
     float alpha, oma;
-    int64_t q, q_tiles;   // q_tiles = work tiles of ncta*128 rows
-    int ncta;             // 1 or 2 (CTA pairs)
+    int64_t q, q_tiles;   // q_tiles = work tiles of 256 rows
     int parts;
     int64_t rows_per_part;
     int kp;
     uint64_t* cand;
     uint32_t* cnt;
     float* thr;
-    uint32_t* gthr;   // [q_pad]
+    uint32_t* gthr;   // [q_pad] followed (8-byte aligned) by kMaxUnits progress words; the region is zeroed here
     float* qerr;      // [q_pad]
     uint16_t* apack;  // [q_pad][a_cols] followed by qshift [q_pad] floats
-    int num_sms;
+    int units;        // CTA pairs to launch (<= kMaxUnits)
+    int device_sms;   // SMs of the device (the window is only honoured when every CTA is resident)
     float* dbg_scores;
     cudaEvent_t ev_start, ev_stop;  // optional: recorded around the filter kernel only
 };
 
-template <int MODE, int NCTA>
+static inline size_t gthr_region_bytes(int64_t q_pad) {
+    return (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8 + sizeof(unsigned long long) * kMaxUnits;
+}
+
+template <int MODE, int KB_T>
 static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cudaStream_t st) {
     constexpr int BLOCK_N = block_n_for_mode(MODE);
-    constexpr int LOAD_N = BLOCK_N / NCTA;
+    constexpr int LOAD_N = BLOCK_N / 2;
     CUtensorMap map_emb, map_kl;
     memset(&map_emb, 0, sizeof map_emb);
     memset(&map_kl, 0, sizeof map_kl);
@@ -712,31 +725,26 @@ static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cuda
                             CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    constexpr size_t smem = smem_bytes_for(NCTA);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(smem)));
-        attr_set = true;
-    }
+    RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE, KB_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(kSmemBytes)));
     const int64_t items = fl.q_tiles * fl.parts;
-    int64_t units = fl.num_sms / NCTA;
+    int64_t units = fl.units;
     if (units < 1) units = 1;
     if (units > items) units = items;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(units * NCTA));
+    cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (fl.ev_start) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_start, st));
-    RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_filter_kernel<MODE, NCTA>, map_emb, map_kl, fa));
+    RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_filter_kernel<MODE, KB_T>, map_emb, map_kl, fa));
     if (fl.ev_stop) RADAR_CUDA_CHECK(cudaEventRecord(fl.ev_stop, st));
     return RADAR_OK;
 }
@@ -749,7 +757,7 @@ static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
 }
 
 static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches) {
-    const int64_t q_pad = fl.q_tiles * kBlockM * fl.ncta;
+    const int64_t q_pad = fl.q_tiles * kTileQ;
     const int cols = a_cols_for(fl.mode, fl.corpus->d);
     size_t shift_off = (sizeof(uint16_t) * static_cast<size_t>(q_pad) * cols + 255) / 256 * 256;
     float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fl.apack) + shift_off);
@@ -760,21 +768,29 @@ static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches)
     pa.apack = fl.apack; pa.qshift = qshift; pa.qerr = fl.qerr;
     query_pack_kernel<<<static_cast<unsigned>((q_pad * 32 + 255) / 256), 256, 0, st>>>(pa);
     RADAR_CUDA_CHECK(cudaGetLastError());
-    if (fl.parts > 1) RADAR_CUDA_CHECK(cudaMemsetAsync(fl.gthr, 0, sizeof(uint32_t) * q_pad, st));
+    RADAR_CUDA_CHECK(cudaMemsetAsync(fl.gthr, 0, gthr_region_bytes(q_pad), st));
     FilterArgs fa{};
     fa.apack = fl.apack; fa.qshift = qshift; fa.q = fl.q; fa.q_tiles = fl.q_tiles; fa.n = fl.corpus->n;
     fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
     fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.gthr = fl.gthr; fa.dbg_scores = fl.dbg_scores;
+    fa.progress = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(fl.gthr) +
+                                                        (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8);
+    // window: ~16 MB of corpus tiles per slab in flight (a few slabs are swept concurrently; L2 is 126 MB).  Only
+    // when every CTA of the launch is resident at once and at least two query tiles share a slab.
+    const int kblocks = fl.mode != RADAR_MODE_KL ? fl.corpus->d / 64 : 0;
+    const int64_t tile_bytes = 2ll * slot_stride_for(fl.mode, kblocks);
+    int64_t window = (16ll << 20) / tile_bytes;
+    if (window < 4 * kProgressEvery) window = 4 * kProgressEvery;
+    const bool resident = 2 * fl.units <= fl.device_sms;
+    fa.window = (resident && fl.q_tiles > 1 && getenv("RADAR_TC_NO_WINDOW") == nullptr) ? static_cast<int>(window) : 0;
     int rc;
-    if (fl.ncta == 2) {
-        if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR, 2>(fl, fa, st);
-        else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 2>(fl, fa, st);
-        else rc = launch_filter_mode<RADAR_MODE_HYBRID, 2>(fl, fa, st);
-    } else {
-        if (fl.mode == RADAR_MODE_DPR) rc = launch_filter_mode<RADAR_MODE_DPR, 1>(fl, fa, st);
-        else if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 1>(fl, fa, st);
-        else rc = launch_filter_mode<RADAR_MODE_HYBRID, 1>(fl, fa, st);
-    }
+    const bool d512 = fl.corpus->d == 512;
+    if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 0>(fl, fa, st);
+    else if (fl.mode == RADAR_MODE_DPR)
+        rc = d512 ? launch_filter_mode<RADAR_MODE_DPR, 8>(fl, fa, st) : launch_filter_mode<RADAR_MODE_DPR, 0>(fl, fa, st);
+    else
+        rc = d512 ? launch_filter_mode<RADAR_MODE_HYBRID, 8>(fl, fa, st)
+                  : launch_filter_mode<RADAR_MODE_HYBRID, 0>(fl, fa, st);
     if (rc) return rc;
     *launches = 2;
     return RADAR_OK;

@@ -74,7 +74,7 @@ class RadarIndex:
 
     def __init__(self, d: int = 512, device: Union[str, torch.device] = "cuda", precision: str = "bf16",
                  eps: float = 1e-8, normalize: bool = False, idx_offset: int = 0, algo: str = "auto",
-                 overfetch: int = 0, num_sms: int = 0, keep_bf16: bool = True, cta_pairs: bool = True):
+                 overfetch: int = 0, num_sms: int = 0, keep_bf16: bool = True):
         self.d = int(d)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -88,8 +88,6 @@ class RadarIndex:
         self.idx_offset = int(idx_offset)
         self.overfetch, self.num_sms = int(overfetch), int(num_sms)
         self.keep_bf16 = keep_bf16
-        # tensor-core filter form: CTA pairs (tcgen05 cta_group::2, M = 256) or single CTAs (M = 128)
-        self.cta_pairs = bool(cta_pairs) and os.environ.get("RADAR_TC_SINGLE_CTA", "0") != "1"
         self.emb_f32: Optional[torch.Tensor] = None
         self.emb_bf16: Optional[torch.Tensor] = None
         self.logq16: Optional[torch.Tensor] = None
@@ -247,7 +245,6 @@ class RadarIndex:
         sp.precision = L.PREC_BY_NAME[precision or self.precision]
         sp.algo = L.ALGO_BY_NAME[algo or self.algo]
         sp.overfetch, sp.num_sms = self.overfetch, self.num_sms
-        sp.reserved = 0 if self.cta_pairs else 1
         lib = L.lib()
         nbytes = lib.radar_search_workspace_bytes(C.byref(cs), q, C.byref(sp))
         if nbytes == 0:
@@ -284,7 +281,6 @@ class RadarIndex:
         sp.mode, sp.k, sp.alpha = m, min(10, self.ntotal), float(alpha)
         sp.precision, sp.algo = L.PREC_BF16, L.ALGO_TC_FILTER
         sp.num_sms = self.num_sms
-        sp.reserved = 0 if self.cta_pairs else 1
         out = torch.full((q, self.ntotal), float("nan"), dtype=torch.float32, device=self.device)
         nbytes = L.lib().radar_search_workspace_bytes(C.byref(cs), q, C.byref(sp))
         if nbytes == 0:

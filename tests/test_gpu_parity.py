@@ -208,13 +208,12 @@ def test_embedding_dims_other_than_512(dev):
 # ---------------------------------------------------------------------------------------------------
 # tensor-core filter
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("cta_pairs", [True, False])
-def test_tc_filter_keys_match_bf16_products(dev, cta_pairs):
-    """Dense dump of the tcgen05 accumulators (CTA-pair and single-CTA forms) against the same bf16-rounded
-    products in float64."""
+def test_tc_filter_keys_match_bf16_products(dev):
+    """Dense dump of the tcgen05 accumulators (cta_group::2 pairs) against the same bf16-rounded products in
+    float64."""
     from oracle import c_oracle as co
     p = make_problem(1000, 300, seed=10)
-    idx = _index(p, dev, cta_pairs=cta_pairs)
+    idx = _index(p, dev)
     bf = lambda a: torch.from_numpy(np.ascontiguousarray(a)).bfloat16().double().numpy()
     ip = bf(p["q_emb"]) @ bf(p["c_emb"]).T
     keys = idx.debug_filter_keys(p["q_emb"], mode="dpr").cpu().numpy()
@@ -230,12 +229,11 @@ def test_tc_filter_keys_match_bf16_products(dev, cta_pairs):
     assert np.max(np.abs(keys - hyb)) < 2e-4
 
 
-@pytest.mark.parametrize("cta_pairs", [True, False])
 @pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
 @pytest.mark.parametrize("k", [1, 10, 32, 85])
-def test_tc_fp32_mode_is_certified_bit_identical(dev, mode, k, cta_pairs):
+def test_tc_fp32_mode_is_certified_bit_identical(dev, mode, k):
     p = make_problem(30000, 500, seed=12)
-    idx = _index(p, dev, precision="fp32", algo="tc", cta_pairs=cta_pairs)
+    idx = _index(p, dev, precision="fp32", algo="tc")
     s, i = _search(idx, p, mode, k)
     ws, wi = _oracle(p, mode, k)
     assert np.array_equal(i, wi) and np.array_equal(s, ws)
