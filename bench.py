@@ -431,7 +431,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step[0] * args.steps,
             "roofline": roof, "cpu_baseline": cpu,
             "search_stats": {"algo_used": stats.algo_used, "parts": stats.parts, "kprime": stats.kprime,
-                             "uncertified": stats.uncertified, "kernel_launches_per_search": stats.kernel_launches},
+                             "uncertified": stats.uncertified, "kernel_launches_per_search": stats.kernel_launches,
+                             "filter_sm_mhz": round(stats.filter_sm_mhz, 1)},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -112,6 +112,8 @@ typedef struct radar_search_stats {
     int64_t uncertified;     /* FP32/TC_FILTER: queries whose certificate failed and were re-run exactly */
     int32_t parts;           /* corpus slabs per query tile */
     int32_t kprime;          /* candidates kept per query by the filter */
+    float filter_sm_mhz;     /* average SM clock during the tensor-core filter kernel (clock64 / globaltimer), 0 if not run */
+    int32_t reserved;
 } radar_search_stats_t;
 
 const char* radar_last_error(void);

@@ -53,7 +53,7 @@ class SearchParams(C.Structure):
 class SearchStats(C.Structure):
     _fields_ = [
         ("algo_used", C.c_int32), ("kernel_launches", C.c_int32), ("uncertified", C.c_int64),
-        ("parts", C.c_int32), ("kprime", C.c_int32),
+        ("parts", C.c_int32), ("kprime", C.c_int32), ("filter_sm_mhz", C.c_float), ("reserved", C.c_int32),
     ]
 
 

@@ -352,6 +352,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
     const float oma = 1.0f - alpha;
     int launches = 0;
     int64_t uncertified = 0;
+    unsigned long long* clk_dev = nullptr;
 
     if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
         ScanArgs a{};
@@ -389,6 +390,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         int nl = 0;
         rc = tc::launch_filter(fl, st, &nl);
         if (rc) return rc;
+        clk_dev = fl.clk_dev;
         launches += nl;
         select_kernel<<<static_cast<unsigned>(q), kSelThreads, 0, st>>>(cand, cnt, thr, pl.parts, kCandCap, pl.R, sel,
                                                                        bound);
@@ -451,6 +453,12 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         stats->uncertified = uncertified;
         stats->parts = pl.parts;
         stats->kprime = pl.kp;
+        if (clk_dev) {
+            unsigned long long h[2] = {0, 0};
+            RADAR_CUDA_CHECK(cudaMemcpyAsync(h, clk_dev, sizeof h, cudaMemcpyDeviceToHost, st));
+            RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (h[1] > 0) stats->filter_sm_mhz = static_cast<float>(1e3 * static_cast<double>(h[0]) / static_cast<double>(h[1]));
+        }
     }
     return RADAR_OK;
 }

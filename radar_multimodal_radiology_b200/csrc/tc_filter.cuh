@@ -261,6 +261,10 @@ struct FilterArgs {
     unsigned long long* progress;  // [units] (round << 32 | tiles loaded) of every pair; zeroed before the launch
     int window;         // tiles a pair may run ahead of the slowest pair sweeping the same slab (0 = unbounded)
     float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
+    int dbg_flags;      // measurement aid (RADAR_TC_DBG, results are garbage): 1 = epilogue only recycles the
+                        // accumulators, 2 = no TMA loads (MMAs run on whatever is in shared memory), 4 = epilogue
+                        // loads the accumulators but does not look at them
+    unsigned long long* clk;  // [2] SM cycles / nanoseconds CTA 0 spent in the kernel (average SM clock of the launch)
 };
 
 // cluster helpers (CTA pairs)
@@ -370,6 +374,11 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     const int64_t units = gridDim.x >> 1;
     const int64_t items = a.q_tiles * a.parts;
 
+    unsigned long long clk0 = 0, ns0 = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        clk0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
     if (warp == 0 && lane == 0) {
         if (HAS_IP) prefetch_tmap(&map_emb);
         if (HAS_KL) prefetch_tmap(&map_kl);
@@ -430,7 +439,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     }
                 }
                 mbar_wait(&empty_bar[slot], sph ^ 1);
-                if (elect_one()) {
+                if (a.dbg_flags & 2) {
+                    if (leader && lane == 0)
+                        for (int g = 0; g < groups; ++g) mbar_arrive(&full_bar[slot * kMaxGroups + g]);
+                } else if (elect_one()) {
                     const uint32_t dst = ring_addr + slot * slot_stride;
                     const uint32_t fb = smem_u32(&full_bar[slot * kMaxGroups]);
                     const int my_row = static_cast<int>(row0) + static_cast<int>(cta_rank) * LOAD_N;
@@ -577,31 +589,64 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N;
+                // The whole accumulator row goes to registers with back-to-back tcgen05.ld, then the TMEM stage is
+                // handed back to the MMA issuer BEFORE the values are looked at: the threshold filter below (and its
+                // occasional candidate insertions / compactions) overlaps the next tile's MMAs instead of sitting
+                // between two of them.
+                float v[BLOCK_N];
+                if (!(a.dbg_flags & 1)) {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N; c += 32) {
+                        if (BLOCK_N - c >= 32) tmem_ld_x32(t_acc + c, v + c);
+                        else tmem_ld_x16(t_acc + c, v + c);
+                    }
+                    tmem_wait_ld();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+                if (++as == ACC_STAGES) {
+                    as = 0;
+                    aph ^= 1;
+                }
+                if (a.dbg_flags & 5) {
+                    if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[BLOCK_N - 1]));
+                    continue;
+                }
+                if (a.dbg_scores && valid) {
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N; ++j)
+                        if (row0 + j < a.n) a.dbg_scores[qrow * a.n + row0 + j] = v[j] - shift;
+                }
 #pragma unroll
                 for (int c = 0; c < BLOCK_N; c += 32) {
-                    constexpr int kFull = 32;
-                    const int width = (BLOCK_N - c) < kFull ? (BLOCK_N - c) : kFull;  // 32 or 16 (compile time after unroll)
-                    float v[32];
-                    if (width == 32) tmem_ld_x32(t_acc + c, v);
-                    else tmem_ld_x16(t_acc + c, v);
-                    tmem_wait_ld();
-                    float m = v[0];
+                    constexpr int kGroup = 8;
+                    const int width = (BLOCK_N - c) < 32 ? (BLOCK_N - c) : 32;  // 32 or 16 (compile time after unroll)
+                    float gm[4];
 #pragma unroll
-                    for (int j = 1; j < 32; ++j)
-                        if (j < width) m = fmaxf(m, v[j]);
-                    if (a.dbg_scores && valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (j < width && row0 + c + j < a.n) a.dbg_scores[qrow * a.n + row0 + c + j] = v[j] - shift;
+                    for (int g = 0; g < 4; ++g) {
+                        if (g * kGroup < width) {
+                            const float* w = v + c + g * kGroup;
+                            gm[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
+                        } else {
+                            gm[g] = -CUDART_INF_F;
+                        }
                     }
+                    const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
                     const bool hit = m >= thr_cmp;
                     if (__any_sync(0xffffffffu, hit)) {
                         if (hit) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                if (j < width && v[j] >= thr_cmp) {
-                                    const int64_t row = row0 + c + j;
-                                    if (row < row_end) buf[cnt++] = make_composite(__fsub_rn(v[j], shift), static_cast<uint32_t>(row));
+                            for (int g = 0; g < 4; ++g) {
+                                if (g * kGroup < width && gm[g] >= thr_cmp) {
+#pragma unroll
+                                    for (int j = 0; j < kGroup; ++j) {
+                                        const float x = v[c + g * kGroup + j];
+                                        if (x >= thr_cmp) {
+                                            const int64_t row = row0 + c + g * kGroup + j;
+                                            if (row < row_end) buf[cnt++] = make_composite(__fsub_rn(x, shift), static_cast<uint32_t>(row));
+                                        }
+                                    }
                                 }
                             }
                         }
@@ -622,13 +667,6 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
-                if (++as == ACC_STAGES) {
-                    as = 0;
-                    aph ^= 1;
-                }
             }
             a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
             a.thr[qrow * a.parts + part] = thr;
@@ -639,6 +677,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     __syncthreads();
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
     if (warp == 1) tmem_dealloc_pair(tmem_base);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ns1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+        a.clk[0] = clock64() - clk0;
+        a.clk[1] = ns1 - ns0;
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -701,10 +745,11 @@ struct FilterLaunch {
     int device_sms;   // SMs of the device (the window is only honoured when every CTA is resident)
     float* dbg_scores;
     cudaEvent_t ev_start, ev_stop;  // optional: recorded around the filter kernel only
+    unsigned long long* clk_dev;    // out: device address of the {cycles, ns} pair the kernel writes
 };
 
 static inline size_t gthr_region_bytes(int64_t q_pad) {
-    return (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8 + sizeof(unsigned long long) * kMaxUnits;
+    return (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8 + sizeof(unsigned long long) * (kMaxUnits + 2);
 }
 
 template <int MODE, int KB_T>
@@ -756,7 +801,7 @@ static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
     return b + sizeof(float) * static_cast<size_t>(q_pad);
 }
 
-static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches) {
+static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     const int64_t q_pad = fl.q_tiles * kTileQ;
     const int cols = a_cols_for(fl.mode, fl.corpus->d);
     size_t shift_off = (sizeof(uint16_t) * static_cast<size_t>(q_pad) * cols + 255) / 256 * 256;
@@ -773,8 +818,11 @@ static int launch_filter(const FilterLaunch& fl, cudaStream_t st, int* launches)
     fa.apack = fl.apack; fa.qshift = qshift; fa.q = fl.q; fa.q_tiles = fl.q_tiles; fa.n = fl.corpus->n;
     fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
     fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.gthr = fl.gthr; fa.dbg_scores = fl.dbg_scores;
+    fa.dbg_flags = getenv("RADAR_TC_DBG") ? atoi(getenv("RADAR_TC_DBG")) : 0;
     fa.progress = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(fl.gthr) +
                                                         (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8);
+    fa.clk = fa.progress + kMaxUnits;
+    fl.clk_dev = fa.clk;
     // window: ~16 MB of corpus tiles per slab in flight (a few slabs are swept concurrently; L2 is 126 MB).  Only
     // when every CTA of the launch is resident at once and at least two query tiles share a slab.
     const int kblocks = fl.mode != RADAR_MODE_KL ? fl.corpus->d / 64 : 0;

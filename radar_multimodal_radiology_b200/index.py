@@ -32,6 +32,7 @@ class SearchStats:
     uncertified: int = 0
     parts: int = 0
     kprime: int = 0
+    filter_sm_mhz: float = 0.0
 
 
 def _as_device_f32(x: ArrayLike, device: torch.device) -> torch.Tensor:
@@ -258,7 +259,7 @@ class RadarIndex:
         L.check(rc, "radar_search")
         if stats is not None:
             self.last_stats = SearchStats(stats.algo_used, stats.kernel_launches, int(stats.uncertified),
-                                          stats.parts, stats.kprime)
+                                          stats.parts, stats.kprime, float(stats.filter_sm_mhz))
         return out_s, out_i
 
     def debug_filter_keys(self, x, query_probs=None, mask=None, alpha=0.5, mode=None) -> torch.Tensor:
