@@ -77,7 +77,11 @@ __device__ __forceinline__ uint32_t composite_row(uint64_t c) {
 // `nthreads` threads (ids tid in [0,nthreads)) cooperate; `sync()` must synchronise exactly them.
 template <typename SyncFn>
 __device__ __forceinline__ void bitonic_sort_desc(uint64_t* s, int n, int tid, int nthreads, SyncFn sync) {
+    // the two stage loops stay rolled: callers are rare-path code whose size must not evict hot loops from the
+    // instruction cache (fully unrolled, one 256-element sort was 27 KB of SASS)
+#pragma unroll 1
     for (int size = 2; size <= n; size <<= 1) {
+#pragma unroll 1
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             sync();
             for (int t = tid; t < (n >> 1); t += nthreads) {

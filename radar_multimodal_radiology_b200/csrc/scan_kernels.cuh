@@ -48,8 +48,8 @@ constexpr size_t kScanSmemBytes =
     sizeof(uint64_t) * (kScanThreads / 32) * kCandCap;
 
 // warp-cooperative compaction of one candidate buffer: keep the best kp, return the kp-th key.
-__device__ __forceinline__ float warp_compact(uint64_t* __restrict__ buf, int n, int kp, uint64_t* scratch,
-                                              int lane) {
+// (not inlined: it is rare-path code and its callers' hot loops must stay inside the instruction cache)
+__device__ __noinline__ float warp_compact(uint64_t* __restrict__ buf, int n, int kp, uint64_t* scratch, int lane) {
 #pragma unroll
     for (int e = 0; e < kCandCap / 32; ++e) {
         const int i = lane + 32 * e;

@@ -73,7 +73,8 @@ __host__ __device__ constexpr int slots_for(int mode, int kblocks) {
 __host__ __device__ constexpr int groups_for(int kblocks) { return kblocks <= 1 ? 1 : (kblocks + 1) / 2; }
 
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ +
-                              1024 /*barriers*/;
+                              4 * 32 * 32 * sizeof(float) /*chunk staging*/ + 1024 /*barriers*/;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -357,8 +358,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kRingBytes);
-    uint64_t* bars = scratch + 4 * kCandCap;
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kRingBytes);      // [4 warps][kCandCap] compaction scratch
+    float* stage = reinterpret_cast<float*>(scratch + 4 * kCandCap);          // [4 warps][32 columns][32 lanes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * 32 * 32);
     uint64_t* full_bar = bars;                                   // [kMaxSlots][kMaxGroups] (only the leader's are waited on)
     uint64_t* empty_bar = full_bar + kMaxSlots * kMaxGroups;      // [kMaxSlots]
     uint64_t* tfull_bar = empty_bar + kMaxSlots;                  // [ACC_STAGES]
@@ -544,6 +546,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
         const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         uint64_t* my_scratch = scratch + (warp - 2) * kCandCap;
+        float* my_stage = stage + (warp - 2) * 32 * 32 + lane;  // [column * 32]: bank == lane, no conflicts
         const int a_cols = a_cols_for(MODE, a.d);  // bf16 per packed row
         uint32_t as = 0, aph = 0;
         for (int64_t item = unit; item < items; item += units) {
@@ -613,42 +616,36 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[BLOCK_N - 1]));
                     continue;
                 }
-                if (a.dbg_scores && valid) {
-#pragma unroll
-                    for (int j = 0; j < BLOCK_N; ++j)
-                        if (row0 + j < a.n) a.dbg_scores[qrow * a.n + row0 + j] = v[j] - shift;
-                }
 #pragma unroll
                 for (int c = 0; c < BLOCK_N; c += 32) {
-                    constexpr int kGroup = 8;
                     const int width = (BLOCK_N - c) < 32 ? (BLOCK_N - c) : 32;  // 32 or 16 (compile time after unroll)
-                    float gm[4];
+                    float m = v[c];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (g * kGroup < width) {
-                            const float* w = v + c + g * kGroup;
-                            gm[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
-                        } else {
-                            gm[g] = -CUDART_INF_F;
-                        }
-                    }
-                    const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-                    const bool hit = m >= thr_cmp;
-                    if (__any_sync(0xffffffffu, hit)) {
-                        if (hit) {
+                    for (int jj = 1; jj < 32; ++jj)
+                        if (jj < width) m = fmaxf(m, v[c + jj]);
+                    if (__any_sync(0xffffffffu, m >= thr_cmp) || a.dbg_scores) {
+                        // rare path, written for a small instruction footprint (it used to be unrolled per column and
+                        // pushed the kernel far beyond the instruction cache): the chunk is staged in this warp's
+                        // shared-memory scratch together with a survivor bit mask, then a short loop walks the set bits
+                        uint32_t mask = 0;
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) {
-                                if (g * kGroup < width && gm[g] >= thr_cmp) {
-#pragma unroll
-                                    for (int j = 0; j < kGroup; ++j) {
-                                        const float x = v[c + g * kGroup + j];
-                                        if (x >= thr_cmp) {
-                                            const int64_t row = row0 + c + g * kGroup + j;
-                                            if (row < row_end) buf[cnt++] = make_composite(__fsub_rn(x, shift), static_cast<uint32_t>(row));
-                                        }
-                                    }
-                                }
+                        for (int jj = 0; jj < 32; ++jj) {
+                            if (jj < width) {
+                                my_stage[jj * 32] = v[c + jj];
+                                mask |= (v[c + jj] >= thr_cmp ? 1u : 0u) << jj;
                             }
+                        }
+                        if (a.dbg_scores && valid) {
+                            for (int jj = 0; jj < width; ++jj)
+                                if (row0 + c + jj < a.n) a.dbg_scores[qrow * a.n + row0 + c + jj] = my_stage[jj * 32] - shift;
+                        }
+                        const int64_t row_base = row0 + c;
+                        while (mask) {
+                            const int jj = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int64_t row = row_base + jj;
+                            if (row < row_end)
+                                buf[cnt++] = make_composite(__fsub_rn(my_stage[jj * 32], shift), static_cast<uint32_t>(row));
                         }
                         __syncwarp();
                         unsigned need = __ballot_sync(0xffffffffu, cnt > kCandSoft);
