@@ -72,8 +72,8 @@ __host__ __device__ constexpr int slots_for(int mode, int kblocks) {
 }
 __host__ __device__ constexpr int groups_for(int kblocks) { return kblocks <= 1 ? 1 : (kblocks + 1) / 2; }
 
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 4 * kCandCap * sizeof(uint64_t) /*compaction scratch*/ +
-                              4 * 32 * 32 * sizeof(float) /*chunk staging*/ + 1024 /*barriers*/;
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 4 * 32 * 32 * sizeof(float) /*chunk staging*/ +
+                              1024 /*barriers*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -358,8 +358,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(smem + kRingBytes);      // [4 warps][kCandCap] compaction scratch
-    float* stage = reinterpret_cast<float*>(scratch + 4 * kCandCap);          // [4 warps][32 columns][32 lanes]
+    float* stage = reinterpret_cast<float*>(smem + kRingBytes);               // [4 warps][32 columns][32 lanes]
     uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * 32 * 32);
     uint64_t* full_bar = bars;                                   // [kMaxSlots][kMaxGroups] (only the leader's are waited on)
     uint64_t* empty_bar = full_bar + kMaxSlots * kMaxGroups;      // [kMaxSlots]
@@ -545,7 +544,6 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
-        uint64_t* my_scratch = scratch + (warp - 2) * kCandCap;
         float* my_stage = stage + (warp - 2) * 32 * 32 + lane;  // [column * 32]: bank == lane, no conflicts
         const int a_cols = a_cols_for(MODE, a.d);  // bf16 per packed row
         uint32_t as = 0, aph = 0;
@@ -655,7 +653,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                             uint64_t* b = reinterpret_cast<uint64_t*>(
                                 __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src_lane));
                             const int n_src = __shfl_sync(0xffffffffu, cnt, src_lane);
-                            const float t = warp_compact(b, n_src, a.kp, my_scratch, lane);
+                            const float t = warp_compact(b, n_src, a.kp, lane);
                             if (lane == src_lane) {
                                 thr = t;
                                 thr_cmp = __fadd_rn(t, shift);
