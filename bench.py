@@ -306,13 +306,17 @@ def main():
     need_flush = n_local * bytes_per_corpus_row(mode) <= 2.6e8
     launches_per_step = [0]
 
-    def step_device():
+    def step_device(collect_stats=False):
+        """one step; statistics (which force a stream sync inside the call) are only collected outside the timed region"""
         launches = 0
         out = None
         for r in range(rounds):
-            out = index.search(q_emb, k, query_probs=q_pr, mask=masks[r], alpha=ALPHA, mode=mode, collect_stats=True)
-            launches += ri.last_stats.kernel_launches + (1 if mode != "dpr" else 0) + (1 if world > 1 else 0)
-        launches_per_step[0] = launches
+            out = index.search(q_emb, k, query_probs=q_pr, mask=masks[r], alpha=ALPHA, mode=mode,
+                               collect_stats=collect_stats)
+            if collect_stats:  # radar_search's own kernels + query preparation + the merge kernel after the all-gather
+                launches += ri.last_stats.kernel_launches + (1 if mode != "dpr" else 0) + (1 if world > 1 else 0)
+        if collect_stats:
+            launches_per_step[0] = launches
         return out
 
     def step_e2e():
@@ -360,6 +364,7 @@ def main():
     # ---- warm-up, then the timed regions ---------------------------------------------------------------------
     for _ in range(max(3, args.warmup)):
         step_device()
+    step_device(collect_stats=True)
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
                            os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
@@ -368,6 +373,7 @@ def main():
         time.sleep(0.3)
     total_ms, kern_ms = timed(step_device, args.steps, kernel_events=True)
     clocks = sampler.stop() if rank == 0 else None
+    step_device(collect_stats=True)  # in-kernel clock of a launch made while the device is still under load
     stats = ri.last_stats
     e2e = None
     if not args.no_e2e:

@@ -365,8 +365,8 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         if (rc) return rc;
         if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
         ++launches;
-        select_kernel<<<static_cast<unsigned>(q), kSelThreads, 0, st>>>(cand, cnt, nullptr, pl.parts, kCandCap, pl.R,
-                                                                       sel, nullptr);
+        select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
+            cand, cnt, nullptr, q, pl.parts, kCandCap, pl.R, sel, nullptr);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         FinalArgs f{};
@@ -392,15 +392,17 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         if (rc) return rc;
         clk_dev = fl.clk_dev;
         launches += nl;
-        select_kernel<<<static_cast<unsigned>(q), kSelThreads, 0, st>>>(cand, cnt, thr, pl.parts, kCandCap, pl.R, sel,
-                                                                       bound);
+        select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
+            cand, cnt, thr, q, pl.parts, kCandCap, pl.R, sel, bound);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         RescoreArgs r{};
         r.q_emb = queries->emb_f32; r.p16 = queries->p16; r.entropy = queries->entropy;
         r.c_emb = corpus->emb_f32; r.logq16 = corpus->logq16; r.qmap = nullptr; r.nq = q; r.d = corpus->d;
         r.mode = params->mode; r.alpha = alpha; r.oma = oma; r.R = pl.R; r.sel = sel;
-        rescore_kernel<<<static_cast<unsigned>(ceil_div64(q * pl.R, 256)), 256, 0, st>>>(r);
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kRescoreSmemBytes)));
+        rescore_kernel<<<static_cast<unsigned>(ceil_div64(q, kRsWarps)), kRsWarps * 32, kRescoreSmemBytes, st>>>(r);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         FinalArgs f{};
@@ -433,8 +435,8 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
                 a.cand = fb_cand; a.cnt = fb_cnt;
                 rc = launch_scan(a, ceil_div64(nb, kScanTQ), st);
                 if (rc) return rc;
-                select_kernel<<<static_cast<unsigned>(nb), kSelThreads, 0, st>>>(fb_cand, fb_cnt, nullptr, pl.fb_parts,
-                                                                                kCandCap, params->k, fb_sel, nullptr);
+                select_kernel<<<static_cast<unsigned>(ceil_div64(nb, kSelWarps)), kSelWarps * 32, 0, st>>>(
+                    fb_cand, fb_cnt, nullptr, nb, pl.fb_parts, kCandCap, params->k, fb_sel, nullptr);
                 RADAR_CUDA_CHECK(cudaGetLastError());
                 FinalArgs g{};
                 g.sel = fb_sel; g.R = params->k; g.k = params->k; g.mode = params->mode; g.sort = 0;

@@ -256,54 +256,55 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
 // select: per query, the best R composites over all slabs, sorted descending, into sel[qi][R] (0 = empty).
 // bound[qi] = upper bound on the key of every candidate that was ever dropped for this query
 // (-inf when nothing was dropped): max over slabs of the slab's final threshold, and of anything
-// dropped here.  One CTA per query.
+// dropped here.  One warp per query.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kSelThreads = 256;
-constexpr int kSelCap = 2048;  // shared-memory working set (composites)
+constexpr int kSelWarps = 8;  // queries per CTA (one warp each)
 
-__global__ void __launch_bounds__(kSelThreads) select_kernel(const uint64_t* __restrict__ cand,
-                                                             const uint32_t* __restrict__ cnt,
-                                                             const float* __restrict__ thr_final, int parts,
-                                                             int cap, int R, uint64_t* __restrict__ sel,
-                                                             float* __restrict__ bound) {
-    __shared__ uint64_t s[kSelCap];
-    __shared__ float s_bound;
-    const int64_t qi = blockIdx.x;
-    const int tid = threadIdx.x;
-    auto sync = [] { __syncthreads(); };
-    if (tid == 0) {
-        float b = -CUDART_INF_F;
-        if (thr_final)
-            for (int p = 0; p < parts; ++p) b = fmaxf(b, thr_final[qi * parts + p]);
-        s_bound = b;
+__global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* __restrict__ cand,
+                                                                const uint32_t* __restrict__ cnt,
+                                                                const float* __restrict__ thr_final, int64_t nq,
+                                                                int parts, int cap, int R, uint64_t* __restrict__ sel,
+                                                                float* __restrict__ bound) {
+    __shared__ uint64_t work[kSelWarps][kCandCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
+    if (qi >= nq) return;  // warp-uniform
+    uint64_t* w = work[warp];
+    float b = -CUDART_INF_F;
+    if (thr_final) {
+        for (int p = lane; p < parts; p += 32) b = fmaxf(b, thr_final[qi * parts + p]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
     }
-    __syncthreads();
-
-    int fill = 0;  // uniform across the CTA
+    // the slabs' buffers stream through a kCandCap-entry working set; whenever it fills up the register radix
+    // select keeps the best R (everything it drops has key <= the returned R-th key)
+    int fill = 0;
     for (int p = 0; p < parts; ++p) {
         const int c = static_cast<int>(cnt[qi * parts + p]);
         const uint64_t* src = cand + (qi * parts + p) * cap;
         int done = 0;
         while (done < c) {
-            const int take = min(c - done, kSelCap - fill);
-            for (int i = tid; i < take; i += kSelThreads) s[fill + i] = src[done + i];
+            const int take = min(c - done, kCandCap - fill);
+            for (int i = lane; i < take; i += 32) w[fill + i] = src[done + i];
             fill += take;
             done += take;
-            if (fill == kSelCap) {
-                bitonic_sort_desc(s, kSelCap, tid, kSelThreads, sync);
-                if (tid == 0 && s[R] != 0ull) s_bound = fmaxf(s_bound, composite_key(s[R]));
-                __syncthreads();
+            if (fill == kCandCap) {
+                __syncwarp();
+                b = fmaxf(b, warp_compact(w, fill, R, lane));
                 fill = R;
             }
         }
     }
+    __syncwarp();
+    if (fill > R) {
+        b = fmaxf(b, warp_compact(w, fill, R, lane));
+        fill = R;
+    }
     const int P = max(next_pow2(fill), 2);
-    for (int i = fill + tid; i < P; i += kSelThreads) s[i] = 0ull;
-    bitonic_sort_desc(s, P, tid, kSelThreads, sync);
-    if (tid == 0 && fill > R && s[R] != 0ull) s_bound = fmaxf(s_bound, composite_key(s[R]));
-    for (int i = tid; i < R; i += kSelThreads) sel[qi * R + i] = i < fill ? s[i] : 0ull;
-    __syncthreads();
-    if (tid == 0 && bound) bound[qi] = s_bound;
+    for (int i = fill + lane; i < P; i += 32) w[i] = 0ull;
+    bitonic_sort_desc(w, P, lane, 32, [] { __syncwarp(); });
+    for (int i = lane; i < R; i += 32) sel[qi * R + i] = i < fill ? w[i] : 0ull;
+    if (bound && lane == 0) bound[qi] = b;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -325,34 +326,74 @@ struct RescoreArgs {
     uint64_t* sel;
 };
 
-__global__ void __launch_bounds__(256) rescore_kernel(const RescoreArgs a) {
-    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= a.nq * a.R) return;
-    const uint64_t c = a.sel[t];
-    if (c == 0ull) return;
-    const int64_t qi = t / a.R;
+// One warp per query, lanes = candidates.  The embedding rows of the (up to) 32 candidates of a group are fetched
+// COOPERATIVELY -- for every candidate row the warp issues one coalesced 512-byte load (LDG.128 per lane) into a padded
+// shared-memory tile -- and then each lane walks its own row in index order, so the fma chain is the canonical one while
+// HBM/L2 see full-line requests instead of 16-byte strided ones.
+constexpr int kRsWarps = 4;                 // queries per CTA
+constexpr int kRsChunk = 128;               // floats of a row staged per step
+constexpr int kRsLd = kRsChunk + 4;         // padded row pitch: LDS.128 of 32 different rows is conflict free
+constexpr size_t kRescoreSmemBytes = sizeof(float) * kRsWarps * (32 * kRsLd + kRsChunk);
+
+__global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(const RescoreArgs a) {
+    extern __shared__ __align__(16) float rs_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kRsWarps + warp;
+    if (qi >= a.nq) return;  // warp-uniform
+    float* tile = rs_smem + warp * (32 * kRsLd + kRsChunk);
+    float* qrow = tile + 32 * kRsLd;
     const int64_t qid = a.qmap ? a.qmap[qi] : qi;
-    const uint32_t row = composite_row(c);
-    float ip = 0.0f, x = 0.0f, h = 0.0f;
-    if (a.mode != RADAR_MODE_KL) {
-        const float4* qa = reinterpret_cast<const float4*>(a.q_emb + qid * a.d);
-        const float4* ca = reinterpret_cast<const float4*>(a.c_emb + static_cast<int64_t>(row) * a.d);
-        for (int i = 0; i < (a.d >> 2); ++i) {
-            const float4 u = __ldg(qa + i), v = __ldg(ca + i);
-            ip = __fmaf_rn(u.x, v.x, ip);
-            ip = __fmaf_rn(u.y, v.y, ip);
-            ip = __fmaf_rn(u.z, v.z, ip);
-            ip = __fmaf_rn(u.w, v.w, ip);
+    const bool has_ip = a.mode != RADAR_MODE_KL, has_kl = a.mode != RADAR_MODE_DPR;
+    const float h = has_kl ? a.entropy[qid] : 0.0f;
+    for (int g0 = 0; g0 < a.R; g0 += 32) {
+        const int ci = g0 + lane;
+        const uint64_t c = ci < a.R ? a.sel[qi * a.R + ci] : 0ull;
+        const bool live = c != 0ull;
+        const uint32_t row = live ? composite_row(c) : 0u;
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+        if (live_mask == 0u) continue;
+        float ip = 0.0f, x = 0.0f;
+        if (has_ip) {
+            for (int t0 = 0; t0 < a.d; t0 += kRsChunk) {
+                const int w = min(kRsChunk, a.d - t0);  // multiple of 4
+                __syncwarp();
+                if (4 * lane < w)
+                    *reinterpret_cast<float4*>(qrow + 4 * lane) =
+                        __ldg(reinterpret_cast<const float4*>(a.q_emb + qid * a.d + t0) + lane);
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const uint32_t rr = __shfl_sync(0xffffffffu, row, r);
+                    if (((live_mask >> r) & 1u) && 4 * lane < w)
+                        *reinterpret_cast<float4*>(tile + r * kRsLd + 4 * lane) =
+                            __ldg(reinterpret_cast<const float4*>(a.c_emb + static_cast<int64_t>(rr) * a.d + t0) + lane);
+                }
+                __syncwarp();
+                if (live) {
+                    const float* mine = tile + lane * kRsLd;
+                    for (int t = 0; t < w; t += 4) {
+                        const float4 u = *reinterpret_cast<const float4*>(qrow + t);
+                        const float4 v = *reinterpret_cast<const float4*>(mine + t);
+                        ip = __fmaf_rn(u.x, v.x, ip);
+                        ip = __fmaf_rn(u.y, v.y, ip);
+                        ip = __fmaf_rn(u.z, v.z, ip);
+                        ip = __fmaf_rn(u.w, v.w, ip);
+                    }
+                }
+            }
+        }
+        if (live) {
+            if (has_kl) {
+                const float* pp = a.p16 + qid * kObsPad;
+                const float4* ll = reinterpret_cast<const float4*>(a.logq16 + static_cast<int64_t>(row) * kObsPad);
+                const float4 l0 = __ldg(ll), l1 = __ldg(ll + 1), l2 = __ldg(ll + 2), l3 = __ldg(ll + 3);
+                const float lv[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w,
+                                      l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+#pragma unroll
+                for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(pp[j], lv[j], x);
+            }
+            a.sel[qi * a.R + ci] = make_composite(canonical_key(a.mode, ip, x, h, a.alpha, a.oma), row);
         }
     }
-    if (a.mode != RADAR_MODE_DPR) {
-        const float* pp = a.p16 + qid * kObsPad;
-        const float* ll = a.logq16 + static_cast<int64_t>(row) * kObsPad;
-#pragma unroll
-        for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(pp[j], __ldg(ll + j), x);
-        h = a.entropy[qid];
-    }
-    a.sel[t] = make_composite(canonical_key(a.mode, ip, x, h, a.alpha, a.oma), row);
 }
 
 // ---------------------------------------------------------------------------------------------------
