@@ -67,7 +67,8 @@ enum radar_precision {
 enum radar_algo {
     RADAR_ALGO_AUTO = 0,
     RADAR_ALGO_SIMT_EXACT = 1, /* CUDA-core exact scan with canonical arithmetic (always exact) */
-    RADAR_ALGO_TC_FILTER = 2   /* tcgen05 bf16 filter + canonical re-score (+ certificate in FP32 mode) */
+    RADAR_ALGO_TC_FILTER = 2,  /* tcgen05 bf16 filter + canonical re-score (+ certificate in FP32 mode) */
+    RADAR_ALGO_KL_STREAM = 3   /* KL, <= 256 queries, >= 65 536 cases: tcgen05 stream with pooled candidates (HBM-bound) */
 };
 
 /* Corpus shard resident in HBM.  Pointers a mode does not need may be NULL.

@@ -18,12 +18,12 @@ HEADER_PATH = os.path.join(os.path.dirname(_PKG_DIR), "include", "radar_retrieva
 
 MODE_DPR, MODE_KL, MODE_HYBRID = 0, 1, 2
 PREC_BF16, PREC_FP32 = 0, 1
-ALGO_AUTO, ALGO_SIMT_EXACT, ALGO_TC_FILTER = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT_EXACT, ALGO_TC_FILTER, ALGO_KL_STREAM = 0, 1, 2, 3
 NUM_OBS, OBS_PAD, KLPACK, MAX_K = 14, 16, 32, 128
 
 MODE_BY_NAME = {"dpr": MODE_DPR, "kl": MODE_KL, "hybrid": MODE_HYBRID}
 PREC_BY_NAME = {"bf16": PREC_BF16, "fp32": PREC_FP32}
-ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT_EXACT, "tc": ALGO_TC_FILTER}
+ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT_EXACT, "tc": ALGO_TC_FILTER, "kl_stream": ALGO_KL_STREAM}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",

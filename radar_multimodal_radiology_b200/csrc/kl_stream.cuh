@@ -1,0 +1,542 @@
+// kl_stream.cuh -- KL observation retrieval for FEW queries (q <= 256) over a LARGE corpus: the HBM-bound regime
+// ("latency regime": 64 B of log-probabilities per case and pass, AI ~ q/2 flop/B).
+//
+// The general filter (tc_filter.cuh) puts queries on the M side of the MMA and gives every query row a private
+// candidate buffer per corpus slab; with a handful of queries that leaves 7 of 8 epilogue warps idle and lets every
+// slab warm its thresholds up on its own.  Here the roles are swapped and the candidates are pooled:
+//
+//   boot    (CUDA cores)   canonical keys of a strided SAMPLE of 256-row tiles; per query the maximum of every
+//                          sample tile.  The k'-th largest tile maximum is a valid lower bound of the k'-th best key
+//                          of the whole corpus (tile maxima are distinct cases) -> initial thresholds.
+//   stream  (tcgen05)      CTA pairs sweep the corpus once.  A operand = 256 corpus rows of the bf16 [hi|lo] log table
+//                          (TMA -> smem ring), B operand = the packed queries (resident in smem), D = [256 cases x N
+//                          queries] fp32 in TMEM, 512/N accumulator stages.  Epilogue thread = one case: it compares
+//                          its N keys with the per-query thresholds (broadcast LDS) -- one predicate chain and one vote
+//                          per 32 queries -- and only survivors are appended (atomicAdd slot) to ONE pooled buffer per
+//                          query in global memory.  Every 64 appends the appending warp tries a per-query lock
+//                          and folds the new entries into the query's running best-k' list with the register radix
+//                          select; the k'-th key is published with atomicMax and picked up by all warps.
+//   final                  per query: canonical fp32 re-score of every pooled entry, block radix select of the k best,
+//                          sort, certificate (fp32 mode) / overflow check -> uncertified queries are re-run exactly.
+//
+// Algorithmic bytes: 64 B per case (the [hi|lo] row) + outputs.  Roofline: HBM.
+#pragma once
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "scan_kernels.cuh"
+#include "tc_filter.cuh"
+
+namespace radar {
+namespace kls {
+
+using namespace tc;  // PTX wrappers, descriptors, cluster helpers
+
+constexpr int kTileRows = 256;          // corpus rows per MMA tile (128 per CTA)
+constexpr int kSlots = 16;              // smem ring slots of 8 KB (128 rows x 64 B) per CTA
+constexpr int kSlotBytes = 128 * 64;
+constexpr int kMaxN = 256;              // queries per launch (MMA N)
+constexpr int kRefreshEvery = 64;       // appends of a query between threshold refresh attempts
+constexpr int kThrReload = 4;           // tiles between reloads of the published thresholds
+constexpr int kMinRows = 1 << 16;       // smaller corpora use the general path
+constexpr int kBootThreads = 256;
+
+__host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one query's pooled buffer
+    int c = (1 << 20) / n_pad;
+    return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
+}
+__host__ __device__ inline int sample_tiles_for(int n_pad, int64_t tiles) {
+    int64_t s = 32768 / n_pad;
+    if (s < 256) s = 256;
+    if (s > 1024) s = 1024;
+    return static_cast<int>(s < tiles ? s : tiles);
+}
+
+// ---- boot: tile maxima of the canonical KL key over a strided sample of tiles -----------------------------
+struct BootArgs {
+    const float* logq16;   // [n][16]
+    const float* p16;      // [q][16]
+    const float* entropy;  // [q]
+    int64_t n, tiles;      // corpus rows, 256-row tiles
+    int q, sample_tiles;
+    uint32_t* tilemax;     // [q][sample_tiles] ord-encoded keys (0 = no valid row)
+};
+
+__global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a) {
+    __shared__ float ps[kMaxN * kObsPad];
+    __shared__ float hs[kMaxN];
+    __shared__ uint32_t wmax[kBootThreads / 32][kMaxN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < a.q * kObsPad; i += kBootThreads) ps[i] = a.p16[i];
+    for (int i = tid; i < a.q; i += kBootThreads) hs[i] = a.entropy[i];
+    __syncthreads();
+    for (int s = blockIdx.x; s < a.sample_tiles; s += gridDim.x) {
+        const int64_t tile = static_cast<int64_t>(s) * a.tiles / a.sample_tiles;  // strided over the whole corpus
+        const int64_t row = tile * kTileRows + tid;
+        const bool valid = row < a.n;
+        float l[kObsPad];
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.logq16 + (valid ? row : 0) * kObsPad);
+            const float4 l0 = __ldg(src), l1 = __ldg(src + 1), l2 = __ldg(src + 2), l3 = __ldg(src + 3);
+            l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+            l[8] = l2.x; l[9] = l2.y; l[10] = l2.z; l[11] = l2.w; l[12] = l3.x; l[13] = l3.y; l[14] = l3.z; l[15] = l3.w;
+        }
+        for (int qi = 0; qi < a.q; ++qi) {
+            const float* pp = ps + qi * kObsPad;
+            float x = 0.0f;
+#pragma unroll
+            for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(pp[j], l[j], x);
+            const uint32_t o = valid ? f2ord(__fsub_rn(x, hs[qi])) : 0u;
+            const uint32_t m = __reduce_max_sync(0xffffffffu, o);
+            if (lane == 0) wmax[warp][qi] = m;
+        }
+        __syncthreads();
+        for (int qi = tid; qi < a.q; qi += kBootThreads) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int w = 0; w < kBootThreads / 32; ++w) m = max(m, wmax[w][qi]);
+            a.tilemax[static_cast<int64_t>(qi) * a.sample_tiles + s] = m;
+        }
+        __syncthreads();
+    }
+}
+
+// k'-th largest tile maximum per query (one warp per query) -> initial threshold, lowered by the filter error bound
+__global__ void __launch_bounds__(128) kl_boot_threshold_kernel(const uint32_t* __restrict__ tilemax, int q,
+                                                                int sample_tiles, int kp,
+                                                                const float* __restrict__ qerr,
+                                                                uint32_t* __restrict__ gthr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * 4 + warp;
+    if (qi >= q) return;
+    const uint32_t* src = tilemax + static_cast<int64_t>(qi) * sample_tiles;
+    uint32_t key = 0;
+    if (sample_tiles >= kp) {
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = key | (1u << b);
+            int c = 0;
+            for (int i = lane; i < sample_tiles; i += 32) c += src[i] >= trial ? 1 : 0;
+            if (__reduce_add_sync(0xffffffffu, c) >= kp) key = trial;
+        }
+    }
+    if (lane == 0) {
+        uint32_t o = 0;  // 0 = no threshold
+        if (key != 0u) o = f2ord(__fsub_rn(ord2f(key), qerr[qi]));
+        gthr[qi] = o;
+    }
+}
+
+// ---- stream -------------------------------------------------------------------------------------------------
+struct StreamArgs {
+    int64_t n, tiles;
+    int q, n_pad;                // real queries, MMA N (32 / 64 / 128 / 256)
+    int kp, pool_cap;
+    const float* qshift;         // [n_pad] entropy (0 for padding rows)
+    uint32_t* gthr;              // [n_pad] published thresholds, ord-encoded canonical-key units (0 = none)
+    uint32_t* gcnt;              // [n_pad] appended entries per query (may exceed pool_cap: overflow)
+    uint32_t* lock;              // [n_pad]
+    uint32_t* processed;         // [n_pad] pooled entries already folded into the best list
+    uint32_t* best_n;            // [n_pad]
+    uint64_t* best;              // [n_pad][kCandCap] running best-k' list of every query (touched under the lock only)
+    uint64_t* pool;              // [n_pad][pool_cap]
+};
+
+constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
+                                    4 * 32 * 32 * sizeof(float) /*chunk staging*/ + 4 * kMaxN * sizeof(float) /*thresholds*/ +
+                                    kMaxN * sizeof(float) /*entropy*/ + 4 * kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
+                                    1024 /*barriers*/;
+
+// D[tmem] (+)= A[smem] * B[smem]^T, M = 256 across the CTA pair
+__device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// fold the not yet processed pooled entries of query qi into its best-k' list and publish the k'-th key
+// (warp-cooperative; a no-op when another warp holds the query's lock)
+__device__ __noinline__ void refresh_threshold(const StreamArgs& a, int qi, uint64_t* sc, int lane) {
+    uint32_t got = 0;
+    if (lane == 0) got = atomicCAS(a.lock + qi, 0u, 1u) == 0u ? 1u : 0u;
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (!got) return;
+    __threadfence();
+    uint32_t start = ld_relaxed_u32(a.processed + qi);
+    int nb = static_cast<int>(ld_relaxed_u32(a.best_n + qi));
+    const uint32_t end = min(ld_relaxed_u32(a.gcnt + qi), static_cast<uint32_t>(a.pool_cap));
+    uint64_t* best = a.best + static_cast<int64_t>(qi) * kCandCap;
+    const uint64_t* pool = a.pool + static_cast<int64_t>(qi) * a.pool_cap;
+    for (int i = lane; i < nb; i += 32) sc[i] = __ldcg(best + i);
+    float t = 0.0f;
+    bool have = false;
+    int rounds = 0;
+    while (start < end && rounds < 8) {  // bounded: the lock is never held for long
+        const int take = min(static_cast<int>(end - start), kCandCap - nb);
+        for (int i = lane; i < take; i += 32) sc[nb + i] = __ldcg(pool + start + i);  // unwritten slots read as 0
+        nb += take;
+        start += take;
+        ++rounds;
+        __syncwarp();
+        if (nb > a.kp) {
+            t = warp_compact(sc, nb, a.kp, lane);
+            nb = a.kp;
+            have = true;
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < nb; i += 32) __stcg(best + i, sc[i]);
+    __syncwarp();
+    if (lane == 0) {
+        a.processed[qi] = start;
+        a.best_n[qi] = static_cast<uint32_t>(nb);
+        if (have) atomicMax(a.gthr + qi, f2ord(t));
+        __threadfence();
+        atomicExch(a.lock + qi, 0u);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_constant__ CUtensorMap map_q,
+                 const StreamArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;                                                        // [kSlots][8 KB]
+    uint8_t* qtile = ring + kSlots * kSlotBytes;                                 // [n_pad/2 rows][64 B], SW64
+    float* stage = reinterpret_cast<float*>(qtile + 128 * 64);                   // [4 warps][32 cols][32 lanes]
+    float* thr_s = stage + 4 * 32 * 32;                                          // [4 warps][kMaxN] accumulator units
+    float* h_s = thr_s + 4 * kMaxN;                                              // [kMaxN]
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(h_s + kMaxN);                // [4 warps][kCandCap]
+    uint64_t* bars = scratch + 4 * kCandCap;
+    uint64_t* full_bar = bars;                // [kSlots]
+    uint64_t* empty_bar = full_bar + kSlots;  // [kSlots]
+    uint64_t* tfull_bar = empty_bar + kSlots; // [16]
+    uint64_t* tempty_bar = tfull_bar + 16;    // [16]
+    uint64_t* qfull_bar = tempty_bar + 16;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int64_t unit = blockIdx.x >> 1, units = gridDim.x >> 1;
+    const int N = a.n_pad;
+    const int stages = kTmemCols / N;  // accumulator stages (2 .. 16)
+    const uint32_t idesc = make_idesc_mn(kTileRows, N);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&map_kl);
+        prefetch_tmap(&map_q);
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 16; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 8);
+        }
+        mbar_init(qfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(tmem_slot);
+    for (int i = threadIdx.x; i < N; i += kThreads) h_s[i] = a.qshift[i];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tmem_base != 0) {
+        if (threadIdx.x == 0) printf("radar kl_stream: unexpected TMEM base %u\n", tmem_base);
+        __trap();
+    }
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (elect_one()) {
+            if (leader) mbar_expect_tx(qfull_bar, static_cast<uint32_t>(N / 2 * 64) * 2);
+            tma_load_2d_pair(&map_q, smem_u32(qfull_bar), smem_u32(qtile), 0, static_cast<int>(cta_rank) * (N / 2));
+        }
+        __syncwarp();
+        uint32_t slot = 0, sph = 0;
+        for (int64_t t = unit; t < a.tiles; t += units) {
+            mbar_wait(&empty_bar[slot], sph ^ 1);
+            if (elect_one()) {
+                if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes * 2);
+                tma_load_2d_pair(&map_kl, smem_u32(&full_bar[slot]), smem_u32(ring + slot * kSlotBytes), 0,
+                                 static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 128);
+            }
+            __syncwarp();
+            if (++slot == kSlots) {
+                slot = 0;
+                sph ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA) ================================
+        if (leader) {
+            mbar_wait(qfull_bar, 0);
+            tc_fence_after();
+            const uint64_t bdesc = make_smem_desc(smem_u32(qtile), 512, 4);
+            uint32_t slot = 0, sph = 0, as = 0, aph = 0;
+            for (int64_t t = unit; t < a.tiles; t += units) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                mbar_wait(&full_bar[slot], sph);
+                tc_fence_after();
+                const uint64_t adesc = make_smem_desc(smem_u32(ring + slot * kSlotBytes), 512, 4);
+                const uint32_t d_tmem = static_cast<uint32_t>(as * N);
+                if (elect_one()) {
+                    umma_ss_pair(d_tmem, adesc, bdesc, idesc, 0u);      // L_hi . v_hi
+                    umma_ss_pair(d_tmem, adesc + 2, bdesc, idesc, 1u);  // L_lo . v_hi
+                    umma_ss_pair(d_tmem, adesc, bdesc + 2, idesc, 1u);  // L_hi . v_lo
+                    umma_commit_pair(&empty_bar[slot]);
+                    umma_commit_pair(&tfull_bar[as]);
+                }
+                __syncwarp();
+                if (++slot == kSlots) {
+                    slot = 0;
+                    sph ^= 1;
+                }
+                if (++as == static_cast<uint32_t>(stages)) {
+                    as = 0;
+                    aph ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue warps (2..5): thread = corpus row ================================
+        const int quad = warp & 3;
+        const int ew = warp - 2;
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        float* my_stage = stage + ew * 32 * 32 + lane;
+        float* my_thr = thr_s + ew * kMaxN;
+        uint64_t* my_scratch = scratch + ew * kCandCap;
+        const int nq32 = N / 32;  // threshold words per lane
+        // thresholds in accumulator units: key + H
+        uint32_t pending[kMaxN / 32];
+#pragma unroll
+        for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
+        auto commit_thresholds = [&]() {
+#pragma unroll
+            for (int i = 0; i < kMaxN / 32; ++i) {
+                if (i < nq32) {
+                    const int qi = lane + 32 * i;
+                    const float tk = pending[i] ? ord2f(pending[i]) : -CUDART_INF_F;
+                    my_thr[qi] = qi < a.q ? (pending[i] ? __fadd_rn(tk, h_s[qi]) : -CUDART_INF_F) : CUDART_INF_F;
+                }
+            }
+            __syncwarp();
+        };
+        commit_thresholds();
+        uint32_t as = 0, aph = 0, since = 0;
+        for (int64_t t = unit; t < a.tiles; t += units) {
+            if (++since == kThrReload) {  // use the values requested kThrReload tiles ago, request fresh ones
+                since = 0;
+                commit_thresholds();
+#pragma unroll
+                for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
+            }
+            const int64_t row = t * kTileRows + static_cast<int64_t>(cta_rank) * 128 + quad * 32 + lane;
+            const bool row_ok = row < a.n;
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + lane_addr + as * N;
+            int want_refresh = -1;
+            for (int cb = 0; cb < nq32; ++cb) {
+                float v[32];
+                tmem_ld_x32(t_acc + cb * 32, v);
+                tmem_wait_ld();
+                if (cb == nq32 - 1) {  // the accumulator stage is free again once its last columns are in registers
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+                }
+                const float4* th4 = reinterpret_cast<const float4*>(my_thr + cb * 32);
+                bool hit = false;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 th = th4[c4];  // broadcast
+                    hit |= v[4 * c4 + 0] >= th.x;
+                    hit |= v[4 * c4 + 1] >= th.y;
+                    hit |= v[4 * c4 + 2] >= th.z;
+                    hit |= v[4 * c4 + 3] >= th.w;
+                }
+                hit = hit && row_ok;
+                if (__any_sync(0xffffffffu, hit)) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        my_stage[c * 32] = v[c];
+                        mask |= (v[c] >= my_thr[cb * 32 + c] ? 1u : 0u) << c;
+                    }
+                    if (!row_ok) mask = 0;
+                    while (mask) {
+                        const int c = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int qi = cb * 32 + c;
+                        const float key = __fsub_rn(my_stage[c * 32], h_s[qi]);
+                        const uint32_t slot = atomicAdd(a.gcnt + qi, 1u);
+                        if (slot < static_cast<uint32_t>(a.pool_cap))
+                            a.pool[static_cast<int64_t>(qi) * a.pool_cap + slot] = make_composite(key, static_cast<uint32_t>(row));
+                        if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp)) want_refresh = qi;
+                    }
+                    __syncwarp();
+                }
+            }
+            unsigned need = __ballot_sync(0xffffffffu, want_refresh >= 0);
+            while (need) {
+                const int src_lane = __ffs(need) - 1;
+                need &= need - 1;
+                const int qi = __shfl_sync(0xffffffffu, want_refresh, src_lane);
+                refresh_threshold(a, qi, my_scratch, lane);
+            }
+            if (++as == static_cast<uint32_t>(stages)) {
+                as = 0;
+                aph ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem_base);
+}
+
+// ---- final: canonical re-score of the pooled entries, best k, certificate ---------------------------------
+struct StreamFinalArgs {
+    const float* p16;
+    const float* entropy;
+    const float* logq16;
+    const float* qerr;        // [n_pad]
+    const uint32_t* gthr;
+    const uint32_t* gcnt;
+    const uint64_t* pool;
+    int q, k, pool_cap, certify;
+    int64_t idx_offset;
+    float* out_scores;
+    int64_t* out_idx;
+    uint32_t* uncert_count;
+    uint32_t* uncert_list;
+};
+
+constexpr int kFinThreads = 256;
+constexpr int kFinPer = 8192 / kFinThreads;  // pooled entries per thread (registers)
+
+__global__ void __launch_bounds__(kFinThreads) kl_stream_final_kernel(const StreamFinalArgs a) {
+    __shared__ float ps[kObsPad];
+    __shared__ int red[kFinThreads / 32];
+    __shared__ uint64_t top[RADAR_MAX_K * 2];
+    __shared__ int top_n;
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < kObsPad) ps[tid] = a.p16[qi * kObsPad + tid];
+    if (tid == 0) top_n = 0;
+    __syncthreads();
+    const float h = a.entropy[qi];
+    const uint32_t cnt = a.gcnt[qi];
+    const int n_e = static_cast<int>(min(cnt, static_cast<uint32_t>(a.pool_cap)));
+    const uint64_t* pool = a.pool + static_cast<int64_t>(qi) * a.pool_cap;
+    // canonical composites of this thread's entries
+    uint32_t hi[kFinPer], lo[kFinPer];
+#pragma unroll
+    for (int e = 0; e < kFinPer; ++e) {
+        const int i = tid + e * kFinThreads;
+        hi[e] = 0;
+        lo[e] = 0;
+        if (i < n_e) {
+            const uint64_t c = pool[i];
+            if (c != 0ull) {
+                const uint32_t row = composite_row(c);
+                const float4* ll = reinterpret_cast<const float4*>(a.logq16 + static_cast<int64_t>(row) * kObsPad);
+                const float4 l0 = __ldg(ll), l1 = __ldg(ll + 1), l2 = __ldg(ll + 2), l3 = __ldg(ll + 3);
+                const float lv[16] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w,
+                                      l2.x, l2.y, l2.z, l2.w, l3.x, l3.y, l3.z, l3.w};
+                float x = 0.0f;
+#pragma unroll
+                for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(ps[j], lv[j], x);
+                const uint64_t cc = make_composite(__fsub_rn(x, h), row);
+                hi[e] = static_cast<uint32_t>(cc >> 32);
+                lo[e] = static_cast<uint32_t>(cc);
+            }
+        }
+    }
+    // block radix select of the k-th largest composite (64 bits, key word then row word)
+    auto block_count = [&](int c) {
+        c = __reduce_add_sync(0xffffffffu, c);
+        __syncthreads();
+        if (lane == 0) red[warp] = c;
+        __syncthreads();
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < kFinThreads / 32; ++w) s += red[w];
+        return s;
+    };
+    int live = 0;
+#pragma unroll
+    for (int e = 0; e < kFinPer; ++e) live += (hi[e] | lo[e]) != 0u ? 1 : 0;
+    live = block_count(live);
+    const int kk = min(a.k, live);
+    uint32_t key = 0, low = 0;
+    if (kk > 0) {
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = key | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < kFinPer; ++e) c += hi[e] >= trial ? 1 : 0;
+            if (block_count(c) >= kk) key = trial;
+        }
+        int above = 0;
+#pragma unroll
+        for (int e = 0; e < kFinPer; ++e) above += hi[e] > key ? 1 : 0;
+        above = block_count(above);
+        const int need = kk - above;
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = low | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < kFinPer; ++e) c += (hi[e] == key && lo[e] >= trial) ? 1 : 0;
+            if (block_count(c) >= need) low = trial;
+        }
+#pragma unroll
+        for (int e = 0; e < kFinPer; ++e) {
+            if (hi[e] > key || (hi[e] == key && lo[e] >= low)) {
+                const int pos = atomicAdd(&top_n, 1);
+                top[pos] = (static_cast<uint64_t>(hi[e]) << 32) | lo[e];
+            }
+        }
+    }
+    __syncthreads();
+    const int P = max(next_pow2(max(kk, 1)), 2);
+    for (int i = kk + tid; i < P; i += kFinThreads) top[i] = 0ull;
+    bitonic_sort_desc(top, P, tid, kFinThreads, [] { __syncthreads(); });
+    for (int j = tid; j < a.k; j += kFinThreads) {
+        const uint64_t c = j < kk ? top[j] : 0ull;
+        a.out_scores[static_cast<int64_t>(qi) * a.k + j] = c ? api_score_from_key(RADAR_MODE_KL, composite_key(c)) : CUDART_INF_F;
+        a.out_idx[static_cast<int64_t>(qi) * a.k + j] = c ? static_cast<int64_t>(composite_row(c)) + a.idx_offset : -1;
+    }
+    if (tid == 0) {
+        bool ok = cnt <= static_cast<uint32_t>(a.pool_cap) && kk == a.k;  // an overflowed pool may have lost candidates
+        if (ok && a.certify) {
+            // every case that is NOT in the pool had filter key < the final threshold, and |canonical - filter| <= qerr
+            const uint32_t g = a.gthr[qi];
+            if (g != 0u) ok = ord2f(g) + a.qerr[qi] < composite_key(top[a.k - 1]);
+        }
+        if (!ok) {
+            const uint32_t slot = atomicAdd(a.uncert_count, 1u);
+            a.uncert_list[slot] = static_cast<uint32_t>(qi);
+        }
+    }
+}
+
+}  // namespace kls
+}  // namespace radar

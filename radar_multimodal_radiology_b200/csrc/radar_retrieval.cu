@@ -10,6 +10,7 @@
 #include "prep_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "tc_filter.cuh"
+#include "kl_stream.cuh"
 
 namespace radar {
 
@@ -63,6 +64,10 @@ struct Plan {
     // workspace offsets (bytes)
     size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
     size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
+    // KL stream path
+    int n_pad, pool_cap, sample_tiles;
+    int64_t tiles;
+    size_t off_ks_zero, ks_zero_bytes, off_ks_pool, off_ks_best, off_ks_tilemax;
     int fb_parts;
     int64_t fb_rows_per_part;
     size_t total;
@@ -129,12 +134,25 @@ static void plan_parts_filter(int64_t q_tiles, int64_t n, int tile_rows, int uni
     *rows_per_part = tiles_per_part * tile_rows;
 }
 
+static bool kl_stream_supported(const radar_corpus_t* c, int64_t q, int mode, const DeviceInfo& di) {
+    return di.major == 10 && mode == RADAR_MODE_KL && c->klpack && c->logq16 && q >= 1 && q <= kls::kMaxN &&
+           c->n >= kls::kMinRows;
+}
+
 static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p, const DeviceInfo& di,
                      Plan* pl) {
     memset(pl, 0, sizeof *pl);
     const int sms = p->num_sms > 0 ? p->num_sms : di.sms;
     int algo = p->algo;
-    if (algo == RADAR_ALGO_AUTO) algo = tc_supported(c, p->mode, di) ? RADAR_ALGO_TC_FILTER : RADAR_ALGO_SIMT_EXACT;
+    if (algo == RADAR_ALGO_AUTO) {
+        if (kl_stream_supported(c, q, p->mode, di) && p->num_sms == 0) algo = RADAR_ALGO_KL_STREAM;
+        else algo = tc_supported(c, p->mode, di) ? RADAR_ALGO_TC_FILTER : RADAR_ALGO_SIMT_EXACT;
+    }
+    if (algo == RADAR_ALGO_KL_STREAM && !kl_stream_supported(c, q, p->mode, di)) {
+        set_error("RADAR_ALGO_KL_STREAM needs an sm_100 device, KL mode, klpack, 1..%d queries and >= %d cases", kls::kMaxN,
+                  kls::kMinRows);
+        return di.major != 10 ? RADAR_E_ARCH : RADAR_E_ARG;
+    }
     if (algo == RADAR_ALGO_TC_FILTER && !tc_supported(c, p->mode, di)) {
         set_error("RADAR_ALGO_TC_FILTER needs an sm_100 device, emb_bf16 (d %% 64 == 0, d <= 512) and/or klpack");
         return di.major != 10 ? RADAR_E_ARCH : RADAR_E_ARG;
@@ -146,6 +164,39 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         off = align_up(off + bytes, 256);
         return o;
     };
+    if (algo == RADAR_ALGO_KL_STREAM) {
+        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch(p->k);
+        if (pl->kp < p->k) pl->kp = p->k;
+        if (pl->kp > kCandSoft) pl->kp = kCandSoft;
+        pl->R = pl->kp;
+        int n_pad = 32;
+        while (n_pad < q) n_pad <<= 1;
+        pl->n_pad = n_pad;
+        pl->pool_cap = kls::pool_cap_for(n_pad);
+        pl->tiles = ceil_div64(c->n, kls::kTileRows);
+        pl->sample_tiles = kls::sample_tiles_for(n_pad, pl->tiles);
+        pl->units = sms / 2 < 1 ? 1 : sms / 2;
+        pl->tile_q = n_pad;
+        pl->q_tiles = 1;
+        pl->parts = 1;
+        const int64_t qp = n_pad;
+        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * 5 * qp, 256) + sizeof(uint64_t) * qp * pl->pool_cap;
+        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr] then the pools
+        pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * 5 * qp, 256);
+        pl->off_ks_best = carve(sizeof(uint64_t) * qp * kCandCap);
+        pl->off_ks_tilemax = carve(sizeof(uint32_t) * qp * pl->sample_tiles);
+        pl->off_qerr = carve(sizeof(float) * qp);
+        pl->off_ucount = carve(sizeof(uint32_t) * 4);
+        pl->off_ulist = carve(sizeof(uint32_t) * qp);
+        pl->off_apack = carve(tc::apack_bytes(qp, RADAR_MODE_KL, c->d));
+        const int64_t f_tiles = ceil_div64(q, kScanTQ);
+        plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
+        pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
+        pl->off_fb_cnt = carve(sizeof(uint32_t) * f_tiles * kScanTQ * pl->fb_parts);
+        pl->off_fb_sel = carve(sizeof(uint64_t) * q * p->k);
+        pl->total = off;
+        return RADAR_OK;
+    }
     if (algo == RADAR_ALGO_SIMT_EXACT) {
         pl->kp = p->k;
         pl->R = p->k;
@@ -196,7 +247,7 @@ static int validate_search(const radar_corpus_t* c, int64_t q, const radar_searc
     RADAR_ARG_CHECK(p->mode >= RADAR_MODE_DPR && p->mode <= RADAR_MODE_HYBRID, "bad mode %d", p->mode);
     RADAR_ARG_CHECK(p->precision == RADAR_PREC_BF16 || p->precision == RADAR_PREC_FP32, "bad precision %d",
                     p->precision);
-    RADAR_ARG_CHECK(p->algo >= RADAR_ALGO_AUTO && p->algo <= RADAR_ALGO_TC_FILTER, "bad algo %d", p->algo);
+    RADAR_ARG_CHECK(p->algo >= RADAR_ALGO_AUTO && p->algo <= RADAR_ALGO_KL_STREAM, "bad algo %d", p->algo);
     RADAR_ARG_CHECK(q >= 0, "negative query count");
     RADAR_ARG_CHECK(c->n >= 1 && c->n < 0xFFFFFFFFll, "corpus rows %lld out of range [1, 2^32-1)", (long long)c->n);
     RADAR_ARG_CHECK(p->k >= 1 && p->k <= RADAR_MAX_K, "k=%d out of range [1,%d]", p->k, RADAR_MAX_K);
@@ -354,7 +405,102 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
     int64_t uncertified = 0;
     unsigned long long* clk_dev = nullptr;
 
-    if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
+    if (pl.algo == RADAR_ALGO_KL_STREAM) {
+        // ---- few queries, large corpus: pooled-candidate tcgen05 stream (kl_stream.cuh) ------------------------
+        const int64_t qp = pl.n_pad;
+        uint32_t* zero = reinterpret_cast<uint32_t*>(ws + pl.off_ks_zero);
+        uint32_t *gcnt = zero, *lock = zero + qp, *processed = zero + 2 * qp, *best_n = zero + 3 * qp, *gthr = zero + 4 * qp;
+        uint64_t* pool = reinterpret_cast<uint64_t*>(ws + pl.off_ks_pool);
+        uint64_t* best = reinterpret_cast<uint64_t*>(ws + pl.off_ks_best);
+        uint32_t* tilemax = reinterpret_cast<uint32_t*>(ws + pl.off_ks_tilemax);
+        uint16_t* apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
+        const size_t shift_off = align_up(sizeof(uint16_t) * static_cast<size_t>(qp) * RADAR_KLPACK, 256);
+        float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(apack) + shift_off);
+        RADAR_CUDA_CHECK(cudaMemsetAsync(zero, 0, pl.ks_zero_bytes, st));
+        RADAR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(uint32_t) * 4, st));
+        tc::PackArgs pa{};
+        pa.q_emb = nullptr; pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp;
+        pa.d = corpus->d; pa.mode = RADAR_MODE_KL; pa.alpha = alpha; pa.oma = oma;
+        pa.emb_max_norm = corpus->emb_max_norm; pa.logq_max_abs = corpus->logq_max_abs;
+        pa.apack = apack; pa.qshift = qshift; pa.qerr = qerr;
+        tc::query_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        kls::BootArgs ba{};
+        ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.n = corpus->n;
+        ba.tiles = pl.tiles; ba.q = static_cast<int>(q); ba.sample_tiles = pl.sample_tiles; ba.tilemax = tilemax;
+        kls::kl_boot_kernel<<<static_cast<unsigned>(pl.sample_tiles < 2 * di.sms ? pl.sample_tiles : 2 * di.sms),
+                              kls::kBootThreads, 0, st>>>(ba);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        kls::kl_boot_threshold_kernel<<<static_cast<unsigned>(ceil_div64(q, 4)), 128, 0, st>>>(
+            tilemax, static_cast<int>(q), pl.sample_tiles, pl.kp, qerr, gthr);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        CUtensorMap map_kl, map_q;
+        memset(&map_kl, 0, sizeof map_kl);
+        memset(&map_q, 0, sizeof map_q);
+        rc = tc::encode_2d_bf16(&map_kl, corpus->klpack, RADAR_KLPACK, corpus->n, RADAR_KLPACK, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        rc = tc::encode_2d_bf16(&map_q, apack, RADAR_KLPACK, qp, RADAR_KLPACK, static_cast<uint32_t>(qp / 2),
+                                CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+        kls::StreamArgs sa{};
+        sa.n = corpus->n; sa.tiles = pl.tiles; sa.q = static_cast<int>(q); sa.n_pad = pl.n_pad; sa.kp = pl.kp;
+        sa.pool_cap = pl.pool_cap; sa.qshift = qshift; sa.gthr = gthr; sa.gcnt = gcnt; sa.lock = lock;
+        sa.processed = processed; sa.best_n = best_n; sa.best = best; sa.pool = pool;
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(kls::kl_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kls::kStreamSmemBytes)));
+        int64_t units = pl.units;
+        if (units > pl.tiles) units = pl.tiles;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
+        cfg.blockDim = dim3(tc::kThreads);
+        cfg.dynamicSmemBytes = kls::kStreamSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (g_prof_start) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
+        RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kls::kl_stream_kernel, map_kl, map_q, sa));
+        if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
+        kls::StreamFinalArgs fa{};
+        fa.p16 = queries->p16; fa.entropy = queries->entropy; fa.logq16 = corpus->logq16; fa.qerr = qerr; fa.gthr = gthr;
+        fa.gcnt = gcnt; fa.pool = pool; fa.q = static_cast<int>(q); fa.k = params->k; fa.pool_cap = pl.pool_cap;
+        fa.certify = params->precision == RADAR_PREC_FP32 ? 1 : 0; fa.idx_offset = corpus->idx_offset;
+        fa.out_scores = out_scores; fa.out_idx = out_idx; fa.uncert_count = ucount; fa.uncert_list = ulist;
+        kls::kl_stream_final_kernel<<<static_cast<unsigned>(q), kls::kFinThreads, 0, st>>>(fa);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        launches += 5;
+        // queries whose pool overflowed or (fp32 mode) whose certificate failed are re-run by the exact scan
+        uint32_t h_count = 0;
+        RADAR_CUDA_CHECK(cudaMemcpyAsync(&h_count, ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
+        uncertified = h_count;
+        if (h_count > 0) {
+            uint64_t* fb_cand = reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand);
+            uint32_t* fb_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt);
+            uint64_t* fb_sel = reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel);
+            const int64_t nb = h_count;
+            ScanArgs a{};
+            a.q_emb = nullptr; a.p16 = queries->p16; a.entropy = queries->entropy; a.c_emb = nullptr;
+            a.logq16 = corpus->logq16; a.qmap = ulist; a.nq = nb; a.n = corpus->n; a.d = corpus->d;
+            a.mode = RADAR_MODE_KL; a.alpha = alpha; a.oma = oma; a.parts = pl.fb_parts;
+            a.rows_per_part = pl.fb_rows_per_part; a.kp = params->k; a.cand = fb_cand; a.cnt = fb_cnt;
+            rc = launch_scan(a, ceil_div64(nb, kScanTQ), st);
+            if (rc) return rc;
+            select_kernel<<<static_cast<unsigned>(ceil_div64(nb, kSelWarps)), kSelWarps * 32, 0, st>>>(
+                fb_cand, fb_cnt, nullptr, nb, pl.fb_parts, kCandCap, params->k, fb_sel, nullptr);
+            RADAR_CUDA_CHECK(cudaGetLastError());
+            FinalArgs g{};
+            g.sel = fb_sel; g.R = params->k; g.k = params->k; g.mode = RADAR_MODE_KL; g.sort = 0; g.qmap = ulist;
+            g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx;
+            final_kernel<<<static_cast<unsigned>(nb), kFinalThreads, 0, st>>>(g);
+            RADAR_CUDA_CHECK(cudaGetLastError());
+            launches += 3;
+        }
+    } else if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
         ScanArgs a{};
         a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
         a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = nullptr;

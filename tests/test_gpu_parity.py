@@ -262,6 +262,59 @@ def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
 
 
 # ---------------------------------------------------------------------------------------------------
+# KL stream path (few queries, large corpus: pooled candidates, tcgen05 with cases on the M side)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("q", [1, 7, 32, 33, 200])
+@pytest.mark.parametrize("k", [1, 10, 32, 128])
+def test_kl_stream_fp32_is_bit_identical(dev, q, k):
+    p = make_problem(70001, q, d=64, seed=20 + q)
+    idx = _index(p, dev, precision="fp32")
+    s, i = _search(idx, p, "kl", k)
+    assert idx.last_stats.algo_used == 3  # auto picks the stream path here
+    ws, wi = _oracle(p, "kl", k)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    assert idx.last_stats.uncertified <= max(2, q // 4)
+    s2, i2 = _search(idx, p, "kl", k, algo="simt")
+    assert np.array_equal(i2, wi) and np.array_equal(s2, ws)
+
+
+def test_kl_stream_bf16_recall_and_canonical_scores(dev):
+    from oracle import c_oracle as co
+    p = make_problem(300000, 64, d=64, seed=31)
+    idx = _index(p, dev, precision="bf16")
+    for k in (10, 32):
+        s, i = _search(idx, p, "kl", k)
+        assert idx.last_stats.algo_used == 3 and idx.last_stats.uncertified == 0
+        ws, wi = _oracle(p, "kl", k)
+        recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)])
+        assert recall >= 0.999, recall
+        logq = co.prepare_corpus(p["c_pr"])
+        p16, ent = co.prepare_queries(p["q_pr"], p["mask"])
+        canon = co.score_pairs(1, i, p16=p16, entropy=ent, logq16=logq)
+        assert np.array_equal(s, canon)
+
+
+def test_kl_stream_adversarial_order_falls_back_exactly(dev):
+    """Cases sorted from worst to best for query 0: every case beats the running threshold, the pooled buffer
+    overflows, and the query must be re-run by the exact scan -- the result stays bit-identical."""
+    from oracle import c_oracle as co
+    p = make_problem(120000, 5, d=64, seed=33)
+    logq = co.prepare_corpus(p["c_pr"])
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"])
+    x = p16[0].astype(np.float64) @ logq.astype(np.float64).T
+    order = np.argsort(x, kind="stable")  # ascending key = descending KL
+    p["c_pr"] = p["c_pr"][order]
+    p["c_emb"] = p["c_emb"][order]
+    idx = _index(p, dev, precision="bf16")
+    s, i = _search(idx, p, "kl", 10)
+    assert idx.last_stats.algo_used == 3 and idx.last_stats.uncertified >= 1
+    ws, wi = _oracle(p, "kl", 10)
+    assert np.array_equal(i[0], wi[0]) and np.array_equal(s[0], ws[0])
+    recall = np.mean([len(set(a) & set(b)) / 10 for a, b in zip(i, wi)])
+    assert recall >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------
 # merge / re-rank / projection kernels
 # ---------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("parts,k_in,k_out,ascending", [(2, 10, 10, False), (8, 32, 32, False), (8, 32, 5, True),
