@@ -33,47 +33,57 @@ namespace kls {
 
 using namespace tc;  // PTX wrappers, descriptors, cluster helpers
 
-constexpr int kTileRows = 256;          // corpus rows per MMA tile (128 per CTA)
-constexpr int kSlots = 16;              // smem ring slots of 8 KB (128 rows x 64 B) per CTA
-constexpr int kSlotBytes = 128 * 64;
+constexpr int kTileRows = 512;          // corpus rows per super-tile: 256 per CTA = two M = 256 MMA sub-tiles
+constexpr int kSubRows = 256;           // corpus rows per MMA (128 per CTA)
+constexpr int kSlots = 8;               // smem ring slots of 16 KB (256 rows x 64 B) per CTA
+constexpr int kSlotBytes = 256 * 64;
 constexpr int kMaxN = 256;              // queries per launch (MMA N)
+constexpr int kStreamThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1
 constexpr int kRefreshEvery = 64;       // appends of a query between threshold refresh attempts
-constexpr int kThrReload = 4;           // tiles between reloads of the published thresholds
+constexpr int kThrReload = 4;           // super-tiles between reloads of the published thresholds
 constexpr int kMinRows = 1 << 16;       // smaller corpora use the general path
 constexpr int kBootThreads = 256;
+constexpr int kBootRows = 256;          // rows of one sample tile
+constexpr int kMaxSample = 1024;
 
 __host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one query's pooled buffer
     int c = (1 << 20) / n_pad;
     return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
 }
-__host__ __device__ inline int sample_tiles_for(int n_pad, int64_t tiles) {
+__host__ __device__ inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
     int64_t s = 32768 / n_pad;
     if (s < 256) s = 256;
-    if (s > 1024) s = 1024;
-    return static_cast<int>(s < tiles ? s : tiles);
+    if (s > kMaxSample) s = kMaxSample;
+    return static_cast<int>(s < boot_tiles ? s : boot_tiles);
 }
 
-// ---- boot: tile maxima of the canonical KL key over a strided sample of tiles -----------------------------
+// ---- boot: tile maxima of the canonical KL key over a strided sample of 256-row tiles; the last CTA to finish
+// turns them into the initial thresholds (k'-th largest tile maximum per query, lowered by the filter error bound)
 struct BootArgs {
     const float* logq16;   // [n][16]
     const float* p16;      // [q][16]
     const float* entropy;  // [q]
-    int64_t n, tiles;      // corpus rows, 256-row tiles
-    int q, sample_tiles;
+    const float* qerr;     // [q]
+    int64_t n, boot_tiles; // corpus rows, 256-row tiles
+    int q, sample_tiles, kp;
     uint32_t* tilemax;     // [q][sample_tiles] ord-encoded keys (0 = no valid row)
+    uint32_t* done;        // CTA completion counter (zeroed before the launch)
+    uint32_t* gthr;        // [q] out
 };
 
 __global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a) {
-    __shared__ float ps[kMaxN * kObsPad];
+    __shared__ __align__(16) float ps[kMaxN * kObsPad];
     __shared__ float hs[kMaxN];
     __shared__ uint32_t wmax[kBootThreads / 32][kMaxN];
+    __shared__ uint32_t last_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < a.q * kObsPad; i += kBootThreads) ps[i] = a.p16[i];
-    for (int i = tid; i < a.q; i += kBootThreads) hs[i] = a.entropy[i];
+    const int q4 = (a.q + 3) & ~3;
+    for (int i = tid; i < q4 * kObsPad; i += kBootThreads) ps[i] = i < a.q * kObsPad ? a.p16[i] : 0.0f;
+    for (int i = tid; i < q4; i += kBootThreads) hs[i] = i < a.q ? a.entropy[i] : 0.0f;
     __syncthreads();
     for (int s = blockIdx.x; s < a.sample_tiles; s += gridDim.x) {
-        const int64_t tile = static_cast<int64_t>(s) * a.tiles / a.sample_tiles;  // strided over the whole corpus
-        const int64_t row = tile * kTileRows + tid;
+        const int64_t tile = static_cast<int64_t>(s) * a.boot_tiles / a.sample_tiles;  // strided over the whole corpus
+        const int64_t row = tile * kBootRows + tid;
         const bool valid = row < a.n;
         float l[kObsPad];
         {
@@ -82,14 +92,29 @@ __global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a)
             l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
             l[8] = l2.x; l[9] = l2.y; l[10] = l2.z; l[11] = l2.w; l[12] = l3.x; l[13] = l3.y; l[14] = l3.z; l[15] = l3.w;
         }
-        for (int qi = 0; qi < a.q; ++qi) {
-            const float* pp = ps + qi * kObsPad;
-            float x = 0.0f;
+        for (int qi = 0; qi < q4; qi += 4) {  // four independent canonical chains per step
+            float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(pp[j], l[j], x);
-            const uint32_t o = valid ? f2ord(__fsub_rn(x, hs[qi])) : 0u;
-            const uint32_t m = __reduce_max_sync(0xffffffffu, o);
-            if (lane == 0) wmax[warp][qi] = m;
+            for (int j4 = 0; j4 < 4; ++j4) {
+                float4 pv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pv[u] = *reinterpret_cast<const float4*>(ps + (qi + u) * kObsPad + 4 * j4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    x[u] = __fmaf_rn(pv[u].x, l[4 * j4 + 0], x[u]);
+                    x[u] = __fmaf_rn(pv[u].y, l[4 * j4 + 1], x[u]);
+                    if (j4 < 3) {  // observations 14 and 15 are padding
+                        x[u] = __fmaf_rn(pv[u].z, l[4 * j4 + 2], x[u]);
+                        x[u] = __fmaf_rn(pv[u].w, l[4 * j4 + 3], x[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t o = valid ? f2ord(__fsub_rn(x[u], hs[qi + u])) : 0u;
+                const uint32_t m = __reduce_max_sync(0xffffffffu, o);
+                if (lane == 0) wmax[warp][qi + u] = m;
+            }
         }
         __syncthreads();
         for (int qi = tid; qi < a.q; qi += kBootThreads) {
@@ -100,37 +125,38 @@ __global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a)
         }
         __syncthreads();
     }
-}
-
-// k'-th largest tile maximum per query (one warp per query) -> initial threshold, lowered by the filter error bound
-__global__ void __launch_bounds__(128) kl_boot_threshold_kernel(const uint32_t* __restrict__ tilemax, int q,
-                                                                int sample_tiles, int kp,
-                                                                const float* __restrict__ qerr,
-                                                                uint32_t* __restrict__ gthr) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qi = blockIdx.x * 4 + warp;
-    if (qi >= q) return;
-    const uint32_t* src = tilemax + static_cast<int64_t>(qi) * sample_tiles;
-    uint32_t key = 0;
-    if (sample_tiles >= kp) {
-#pragma unroll 1
-        for (int b = 31; b >= 0; --b) {
-            const uint32_t trial = key | (1u << b);
-            int c = 0;
-            for (int i = lane; i < sample_tiles; i += 32) c += src[i] >= trial ? 1 : 0;
-            if (__reduce_add_sync(0xffffffffu, c) >= kp) key = trial;
+    // ---- the last CTA computes the thresholds ----
+    __threadfence();
+    if (tid == 0) last_flag = atomicAdd(a.done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    for (int qi = warp; qi < a.q; qi += kBootThreads / 32) {
+        const uint32_t* src = a.tilemax + static_cast<int64_t>(qi) * a.sample_tiles;
+        uint32_t val[kMaxSample / 32];
+#pragma unroll
+        for (int e = 0; e < kMaxSample / 32; ++e) {
+            const int i = lane + 32 * e;
+            val[e] = i < a.sample_tiles ? __ldcg(src + i) : 0u;
         }
-    }
-    if (lane == 0) {
-        uint32_t o = 0;  // 0 = no threshold
-        if (key != 0u) o = f2ord(__fsub_rn(ord2f(key), qerr[qi]));
-        gthr[qi] = o;
+        uint32_t key = 0;
+        if (a.sample_tiles >= a.kp) {
+#pragma unroll 1
+            for (int b = 31; b >= 0; --b) {
+                const uint32_t trial = key | (1u << b);
+                int c = 0;
+#pragma unroll
+                for (int e = 0; e < kMaxSample / 32; ++e) c += val[e] >= trial ? 1 : 0;
+                if (__reduce_add_sync(0xffffffffu, c) >= a.kp) key = trial;
+            }
+        }
+        if (lane == 0) a.gthr[qi] = key != 0u ? f2ord(__fsub_rn(ord2f(key), a.qerr[qi])) : 0u;  // 0 = no threshold
     }
 }
 
 // ---- stream -------------------------------------------------------------------------------------------------
 struct StreamArgs {
-    int64_t n, tiles;
+    int64_t n, tiles;            // corpus rows, 512-row super-tiles
     int q, n_pad;                // real queries, MMA N (32 / 64 / 128 / 256)
     int kp, pool_cap;
     const float* qshift;         // [n_pad] entropy (0 for padding rows)
@@ -144,9 +170,10 @@ struct StreamArgs {
 };
 
 constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
-                                    4 * 32 * 32 * sizeof(float) /*chunk staging*/ + 4 * kMaxN * sizeof(float) /*thresholds*/ +
-                                    kMaxN * sizeof(float) /*entropy*/ + 4 * kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
+                                    8 * 32 * 32 * sizeof(float) /*chunk staging*/ + 8 * kMaxN * sizeof(float) /*thresholds*/ +
+                                    kMaxN * sizeof(float) /*entropy*/ + 8 * kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
                                     1024 /*barriers*/;
+static_assert(kStreamSmemBytes <= 227 * 1024, "shared memory budget");
 
 // D[tmem] (+)= A[smem] * B[smem]^T, M = 256 across the CTA pair
 __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -161,6 +188,11 @@ __device__ __forceinline__ void umma_ss_pair(uint32_t d_tmem, uint64_t a_desc, u
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
 
@@ -207,23 +239,23 @@ __device__ __noinline__ void refresh_threshold(const StreamArgs& a, int qi, uint
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kStreamThreads, 1)
 kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_constant__ CUtensorMap map_q,
                  const StreamArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* ring = smem;                                                        // [kSlots][8 KB]
+    uint8_t* ring = smem;                                                        // [kSlots][16 KB]
     uint8_t* qtile = ring + kSlots * kSlotBytes;                                 // [n_pad/2 rows][64 B], SW64
-    float* stage = reinterpret_cast<float*>(qtile + 128 * 64);                   // [4 warps][32 cols][32 lanes]
-    float* thr_s = stage + 4 * 32 * 32;                                          // [4 warps][kMaxN] accumulator units
-    float* h_s = thr_s + 4 * kMaxN;                                              // [kMaxN]
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(h_s + kMaxN);                // [4 warps][kCandCap]
-    uint64_t* bars = scratch + 4 * kCandCap;
+    float* stage = reinterpret_cast<float*>(qtile + 128 * 64);                   // [8 warps][32 cols][32 lanes]
+    float* thr_s = stage + 8 * 32 * 32;                                          // [8 warps][kMaxN] accumulator units
+    float* h_s = thr_s + 8 * kMaxN;                                              // [kMaxN]
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(h_s + kMaxN);                // [8 warps][kCandCap]
+    uint64_t* bars = scratch + 8 * kCandCap;
     uint64_t* full_bar = bars;                // [kSlots]
     uint64_t* empty_bar = full_bar + kSlots;  // [kSlots]
-    uint64_t* tfull_bar = empty_bar + kSlots; // [16]
-    uint64_t* tempty_bar = tfull_bar + 16;    // [16]
-    uint64_t* qfull_bar = tempty_bar + 16;    // [1]
+    uint64_t* tfull_bar = empty_bar + kSlots; // [8] one per accumulator stage PAIR
+    uint64_t* tempty_bar = tfull_bar + 8;     // [8] 16 arrivals: 8 epilogue warps x 2 CTAs
+    uint64_t* qfull_bar = tempty_bar + 8;     // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -231,8 +263,8 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     const bool leader = cta_rank == 0;
     const int64_t unit = blockIdx.x >> 1, units = gridDim.x >> 1;
     const int N = a.n_pad;
-    const int stages = kTmemCols / N;  // accumulator stages (2 .. 16)
-    const uint32_t idesc = make_idesc_mn(kTileRows, N);
+    const int spairs = kTmemCols / (2 * N);  // accumulator stage pairs (1 .. 8)
+    const uint32_t idesc = make_idesc_mn(kSubRows, N);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_kl);
@@ -241,15 +273,15 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 8; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8);
+            mbar_init(&tempty_bar[i], 16);
         }
         mbar_init(qfull_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot);
-    for (int i = threadIdx.x; i < N; i += kThreads) h_s[i] = a.qshift[i];
+    for (int i = threadIdx.x; i < N; i += kStreamThreads) h_s[i] = a.qshift[i];
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -261,7 +293,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     }
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
+        // ================================ TMA producer: one 16 KB box (256 rows) per CTA and super-tile ==============
         if (elect_one()) {
             if (leader) mbar_expect_tx(qfull_bar, static_cast<uint32_t>(N / 2 * 64) * 2);
             tma_load_2d_pair(&map_q, smem_u32(qfull_bar), smem_u32(qtile), 0, static_cast<int>(cta_rank) * (N / 2));
@@ -273,7 +305,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             if (elect_one()) {
                 if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes * 2);
                 tma_load_2d_pair(&map_kl, smem_u32(&full_bar[slot]), smem_u32(ring + slot * kSlotBytes), 0,
-                                 static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 128);
+                                 static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 256);
             }
             __syncwarp();
             if (++slot == kSlots) {
@@ -282,43 +314,50 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA) ================================
+        // ================================ MMA issuer (leader CTA): 6 MMAs per super-tile ================================
         if (leader) {
             mbar_wait(qfull_bar, 0);
             tc_fence_after();
             const uint64_t bdesc = make_smem_desc(smem_u32(qtile), 512, 4);
-            uint32_t slot = 0, sph = 0, as = 0, aph = 0;
+            uint32_t slot = 0, sph = 0, sp = 0, aph = 0;
             for (int64_t t = unit; t < a.tiles; t += units) {
-                mbar_wait(&tempty_bar[as], aph ^ 1);
+                mbar_wait(&tempty_bar[sp], aph ^ 1);
                 mbar_wait(&full_bar[slot], sph);
                 tc_fence_after();
                 const uint64_t adesc = make_smem_desc(smem_u32(ring + slot * kSlotBytes), 512, 4);
-                const uint32_t d_tmem = static_cast<uint32_t>(as * N);
+                const uint32_t d0 = static_cast<uint32_t>(sp * 2 * N);
                 if (elect_one()) {
-                    umma_ss_pair(d_tmem, adesc, bdesc, idesc, 0u);      // L_hi . v_hi
-                    umma_ss_pair(d_tmem, adesc + 2, bdesc, idesc, 1u);  // L_lo . v_hi
-                    umma_ss_pair(d_tmem, adesc, bdesc + 2, idesc, 1u);  // L_hi . v_lo
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {  // rows [sub*128, sub*128+128) of each CTA's box
+                        const uint64_t ad = adesc + static_cast<uint64_t>((sub * 128 * 64) >> 4);
+                        const uint32_t d = d0 + static_cast<uint32_t>(sub * N);
+                        umma_ss_pair(d, ad, bdesc, idesc, 0u);      // L_hi . v_hi
+                        umma_ss_pair(d, ad + 2, bdesc, idesc, 1u);  // L_lo . v_hi
+                        umma_ss_pair(d, ad, bdesc + 2, idesc, 1u);  // L_hi . v_lo
+                    }
                     umma_commit_pair(&empty_bar[slot]);
-                    umma_commit_pair(&tfull_bar[as]);
+                    umma_commit_pair(&tfull_bar[sp]);
                 }
                 __syncwarp();
                 if (++slot == kSlots) {
                     slot = 0;
                     sph ^= 1;
                 }
-                if (++as == static_cast<uint32_t>(stages)) {
-                    as = 0;
+                if (++sp == static_cast<uint32_t>(spairs)) {
+                    sp = 0;
                     aph ^= 1;
                 }
             }
         }
     } else {
-        // ================================ epilogue warps (2..5): thread = corpus row ================================
+        // ===================== epilogue warps: thread = corpus row; warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 ====
         const int quad = warp & 3;
-        const int ew = warp - 2;
+        const int ew = warp - 2;           // 0..7
+        const int sub = ew >> 2;           // MMA sub-tile of the super-tile this warp reads
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         float* my_stage = stage + ew * 32 * 32 + lane;
         float* my_thr = thr_s + ew * kMaxN;
+        const uint32_t my_thr_addr = smem_u32(my_thr);
         uint64_t* my_scratch = scratch + ew * kCandCap;
         const int nq32 = N / 32;  // threshold words per lane
         // thresholds in accumulator units: key + H
@@ -337,19 +376,19 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             __syncwarp();
         };
         commit_thresholds();
-        uint32_t as = 0, aph = 0, since = 0;
+        uint32_t sp = 0, aph = 0, since = 0;
         for (int64_t t = unit; t < a.tiles; t += units) {
-            if (++since == kThrReload) {  // use the values requested kThrReload tiles ago, request fresh ones
+            if (++since == kThrReload) {  // use the values requested kThrReload super-tiles ago, request fresh ones
                 since = 0;
                 commit_thresholds();
 #pragma unroll
                 for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
             }
-            const int64_t row = t * kTileRows + static_cast<int64_t>(cta_rank) * 128 + quad * 32 + lane;
+            const int64_t row = t * kTileRows + static_cast<int64_t>(cta_rank) * 256 + sub * 128 + quad * 32 + lane;
             const bool row_ok = row < a.n;
-            mbar_wait(&tfull_bar[as], aph);
+            mbar_wait(&tfull_bar[sp], aph);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + lane_addr + as * N;
+            const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>((sp * 2 + sub) * N);
             int want_refresh = -1;
             for (int cb = 0; cb < nq32; ++cb) {
                 float v[32];
@@ -358,19 +397,18 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 if (cb == nq32 - 1) {  // the accumulator stage is free again once its last columns are in registers
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+                    if (lane == 0) mbar_arrive_leader(&tempty_bar[sp]);
                 }
-                const float4* th4 = reinterpret_cast<const float4*>(my_thr + cb * 32);
-                bool hit = false;
+                bool h0 = false, h1 = false, h2 = false, h3 = false;  // four independent predicate chains
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 th = th4[c4];  // broadcast
-                    hit |= v[4 * c4 + 0] >= th.x;
-                    hit |= v[4 * c4 + 1] >= th.y;
-                    hit |= v[4 * c4 + 2] >= th.z;
-                    hit |= v[4 * c4 + 3] >= th.w;
+                    const float4 th = lds_f4(my_thr_addr + (cb * 32 + 4 * c4) * 4);  // broadcast
+                    h0 |= v[4 * c4 + 0] >= th.x;
+                    h1 |= v[4 * c4 + 1] >= th.y;
+                    h2 |= v[4 * c4 + 2] >= th.z;
+                    h3 |= v[4 * c4 + 3] >= th.w;
                 }
-                hit = hit && row_ok;
+                const bool hit = (h0 | h1 | h2 | h3) && row_ok;
                 if (__any_sync(0xffffffffu, hit)) {
                     uint32_t mask = 0;
 #pragma unroll
@@ -399,8 +437,8 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 const int qi = __shfl_sync(0xffffffffu, want_refresh, src_lane);
                 refresh_threshold(a, qi, my_scratch, lane);
             }
-            if (++as == static_cast<uint32_t>(stages)) {
-                as = 0;
+            if (++sp == static_cast<uint32_t>(spairs)) {
+                sp = 0;
                 aph ^= 1;
             }
         }
@@ -411,7 +449,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     if (warp == 1) tmem_dealloc_pair(tmem_base);
 }
 
-// ---- final: canonical re-score of the pooled entries, best k, certificate ---------------------------------
+// ---- final: survivors of the last published threshold -> canonical re-score -> best k, certificate ---------------
 struct StreamFinalArgs {
     const float* p16;
     const float* entropy;
@@ -429,31 +467,28 @@ struct StreamFinalArgs {
 };
 
 constexpr int kFinThreads = 256;
-constexpr int kFinPer = 8192 / kFinThreads;  // pooled entries per thread (registers)
+constexpr int kFinCap = 2048;  // survivors the sort can take; more (no refresh ever ran and the pool is large) -> exact re-run
 
 __global__ void __launch_bounds__(kFinThreads) kl_stream_final_kernel(const StreamFinalArgs a) {
     __shared__ float ps[kObsPad];
-    __shared__ int red[kFinThreads / 32];
-    __shared__ uint64_t top[RADAR_MAX_K * 2];
-    __shared__ int top_n;
-    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ uint64_t surv[kFinCap];
+    __shared__ int surv_n;
+    const int qi = blockIdx.x, tid = threadIdx.x;
     if (tid < kObsPad) ps[tid] = a.p16[qi * kObsPad + tid];
-    if (tid == 0) top_n = 0;
+    if (tid == 0) surv_n = 0;
     __syncthreads();
     const float h = a.entropy[qi];
     const uint32_t cnt = a.gcnt[qi];
+    const uint32_t g = a.gthr[qi];
     const int n_e = static_cast<int>(min(cnt, static_cast<uint32_t>(a.pool_cap)));
     const uint64_t* pool = a.pool + static_cast<int64_t>(qi) * a.pool_cap;
-    // canonical composites of this thread's entries
-    uint32_t hi[kFinPer], lo[kFinPer];
-#pragma unroll
-    for (int e = 0; e < kFinPer; ++e) {
-        const int i = tid + e * kFinThreads;
-        hi[e] = 0;
-        lo[e] = 0;
-        if (i < n_e) {
-            const uint64_t c = pool[i];
-            if (c != 0ull) {
+    // The final threshold is a lower bound of the k'-th best filter key, so only pooled entries at or above it can be
+    // among the best k' by filter key: everything else was admitted under an older, looser threshold.
+    for (int i = tid; i < n_e; i += kFinThreads) {
+        const uint64_t c = pool[i];
+        if (c != 0ull && static_cast<uint32_t>(c >> 32) >= g) {
+            const int pos = atomicAdd(&surv_n, 1);
+            if (pos < kFinCap) {
                 const uint32_t row = composite_row(c);
                 const float4* ll = reinterpret_cast<const float4*>(a.logq16 + static_cast<int64_t>(row) * kObsPad);
                 const float4 l0 = __ldg(ll), l1 = __ldg(ll + 1), l2 = __ldg(ll + 2), l3 = __ldg(ll + 3);
@@ -462,74 +497,27 @@ __global__ void __launch_bounds__(kFinThreads) kl_stream_final_kernel(const Stre
                 float x = 0.0f;
 #pragma unroll
                 for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(ps[j], lv[j], x);
-                const uint64_t cc = make_composite(__fsub_rn(x, h), row);
-                hi[e] = static_cast<uint32_t>(cc >> 32);
-                lo[e] = static_cast<uint32_t>(cc);
-            }
-        }
-    }
-    // block radix select of the k-th largest composite (64 bits, key word then row word)
-    auto block_count = [&](int c) {
-        c = __reduce_add_sync(0xffffffffu, c);
-        __syncthreads();
-        if (lane == 0) red[warp] = c;
-        __syncthreads();
-        int s = 0;
-#pragma unroll
-        for (int w = 0; w < kFinThreads / 32; ++w) s += red[w];
-        return s;
-    };
-    int live = 0;
-#pragma unroll
-    for (int e = 0; e < kFinPer; ++e) live += (hi[e] | lo[e]) != 0u ? 1 : 0;
-    live = block_count(live);
-    const int kk = min(a.k, live);
-    uint32_t key = 0, low = 0;
-    if (kk > 0) {
-#pragma unroll 1
-        for (int b = 31; b >= 0; --b) {
-            const uint32_t trial = key | (1u << b);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < kFinPer; ++e) c += hi[e] >= trial ? 1 : 0;
-            if (block_count(c) >= kk) key = trial;
-        }
-        int above = 0;
-#pragma unroll
-        for (int e = 0; e < kFinPer; ++e) above += hi[e] > key ? 1 : 0;
-        above = block_count(above);
-        const int need = kk - above;
-#pragma unroll 1
-        for (int b = 31; b >= 0; --b) {
-            const uint32_t trial = low | (1u << b);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < kFinPer; ++e) c += (hi[e] == key && lo[e] >= trial) ? 1 : 0;
-            if (block_count(c) >= need) low = trial;
-        }
-#pragma unroll
-        for (int e = 0; e < kFinPer; ++e) {
-            if (hi[e] > key || (hi[e] == key && lo[e] >= low)) {
-                const int pos = atomicAdd(&top_n, 1);
-                top[pos] = (static_cast<uint64_t>(hi[e]) << 32) | lo[e];
+                surv[pos] = make_composite(__fsub_rn(x, h), row);  // canonical key
             }
         }
     }
     __syncthreads();
-    const int P = max(next_pow2(max(kk, 1)), 2);
-    for (int i = kk + tid; i < P; i += kFinThreads) top[i] = 0ull;
-    bitonic_sort_desc(top, P, tid, kFinThreads, [] { __syncthreads(); });
+    const int ns_all = surv_n;
+    const int ns = min(ns_all, kFinCap);
+    const int P = max(next_pow2(max(ns, 1)), 2);
+    for (int i = ns + tid; i < P; i += kFinThreads) surv[i] = 0ull;
+    bitonic_sort_desc(surv, P, tid, kFinThreads, [] { __syncthreads(); });
     for (int j = tid; j < a.k; j += kFinThreads) {
-        const uint64_t c = j < kk ? top[j] : 0ull;
+        const uint64_t c = j < ns ? surv[j] : 0ull;
         a.out_scores[static_cast<int64_t>(qi) * a.k + j] = c ? api_score_from_key(RADAR_MODE_KL, composite_key(c)) : CUDART_INF_F;
         a.out_idx[static_cast<int64_t>(qi) * a.k + j] = c ? static_cast<int64_t>(composite_row(c)) + a.idx_offset : -1;
     }
     if (tid == 0) {
-        bool ok = cnt <= static_cast<uint32_t>(a.pool_cap) && kk == a.k;  // an overflowed pool may have lost candidates
-        if (ok && a.certify) {
-            // every case that is NOT in the pool had filter key < the final threshold, and |canonical - filter| <= qerr
-            const uint32_t g = a.gthr[qi];
-            if (g != 0u) ok = ord2f(g) + a.qerr[qi] < composite_key(top[a.k - 1]);
+        // an overflowed pool may have lost candidates; too many survivors cannot be sorted here
+        bool ok = cnt <= static_cast<uint32_t>(a.pool_cap) && ns_all <= kFinCap && ns >= a.k;
+        if (ok && a.certify && g != 0u) {
+            // every case that is NOT among the survivors has filter key < the final threshold, |canonical - filter| <= qerr
+            ok = ord2f(g) + a.qerr[qi] < composite_key(surv[a.k - 1]);
         }
         if (!ok) {
             const uint32_t slot = atomicAdd(a.uncert_count, 1u);

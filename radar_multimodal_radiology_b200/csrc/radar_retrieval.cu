@@ -174,15 +174,15 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->n_pad = n_pad;
         pl->pool_cap = kls::pool_cap_for(n_pad);
         pl->tiles = ceil_div64(c->n, kls::kTileRows);
-        pl->sample_tiles = kls::sample_tiles_for(n_pad, pl->tiles);
+        pl->sample_tiles = kls::sample_tiles_for(n_pad, ceil_div64(c->n, kls::kBootRows));
         pl->units = sms / 2 < 1 ? 1 : sms / 2;
         pl->tile_q = n_pad;
         pl->q_tiles = 1;
         pl->parts = 1;
         const int64_t qp = n_pad;
-        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * 5 * qp, 256) + sizeof(uint64_t) * qp * pl->pool_cap;
-        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr] then the pools
-        pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * 5 * qp, 256);
+        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * (5 * qp + 4), 256) + sizeof(uint64_t) * qp * pl->pool_cap;
+        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr | boot counter] then the pools
+        pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * (5 * qp + 4), 256);
         pl->off_ks_best = carve(sizeof(uint64_t) * qp * kCandCap);
         pl->off_ks_tilemax = carve(sizeof(uint32_t) * qp * pl->sample_tiles);
         pl->off_qerr = carve(sizeof(float) * qp);
@@ -426,18 +426,16 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         tc::query_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
         RADAR_CUDA_CHECK(cudaGetLastError());
         kls::BootArgs ba{};
-        ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.n = corpus->n;
-        ba.tiles = pl.tiles; ba.q = static_cast<int>(q); ba.sample_tiles = pl.sample_tiles; ba.tilemax = tilemax;
-        kls::kl_boot_kernel<<<static_cast<unsigned>(pl.sample_tiles < 2 * di.sms ? pl.sample_tiles : 2 * di.sms),
+        ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.qerr = qerr;
+        ba.n = corpus->n; ba.boot_tiles = ceil_div64(corpus->n, kls::kBootRows); ba.q = static_cast<int>(q);
+        ba.sample_tiles = pl.sample_tiles; ba.kp = pl.kp; ba.tilemax = tilemax; ba.done = zero + 5 * qp; ba.gthr = gthr;
+        kls::kl_boot_kernel<<<static_cast<unsigned>(pl.sample_tiles < 4 * di.sms ? pl.sample_tiles : 4 * di.sms),
                               kls::kBootThreads, 0, st>>>(ba);
-        RADAR_CUDA_CHECK(cudaGetLastError());
-        kls::kl_boot_threshold_kernel<<<static_cast<unsigned>(ceil_div64(q, 4)), 128, 0, st>>>(
-            tilemax, static_cast<int>(q), pl.sample_tiles, pl.kp, qerr, gthr);
         RADAR_CUDA_CHECK(cudaGetLastError());
         CUtensorMap map_kl, map_q;
         memset(&map_kl, 0, sizeof map_kl);
         memset(&map_q, 0, sizeof map_q);
-        rc = tc::encode_2d_bf16(&map_kl, corpus->klpack, RADAR_KLPACK, corpus->n, RADAR_KLPACK, 128, CU_TENSOR_MAP_SWIZZLE_64B);
+        rc = tc::encode_2d_bf16(&map_kl, corpus->klpack, RADAR_KLPACK, corpus->n, RADAR_KLPACK, 256, CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
         rc = tc::encode_2d_bf16(&map_q, apack, RADAR_KLPACK, qp, RADAR_KLPACK, static_cast<uint32_t>(qp / 2),
                                 CU_TENSOR_MAP_SWIZZLE_64B);
@@ -452,7 +450,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         if (units > pl.tiles) units = pl.tiles;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
-        cfg.blockDim = dim3(tc::kThreads);
+        cfg.blockDim = dim3(kls::kStreamThreads);
         cfg.dynamicSmemBytes = kls::kStreamSmemBytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -472,7 +470,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         fa.out_scores = out_scores; fa.out_idx = out_idx; fa.uncert_count = ucount; fa.uncert_list = ulist;
         kls::kl_stream_final_kernel<<<static_cast<unsigned>(q), kls::kFinThreads, 0, st>>>(fa);
         RADAR_CUDA_CHECK(cudaGetLastError());
-        launches += 5;
+        launches += 4;
         // queries whose pool overflowed or (fp32 mode) whose certificate failed are re-run by the exact scan
         uint32_t h_count = 0;
         RADAR_CUDA_CHECK(cudaMemcpyAsync(&h_count, ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
