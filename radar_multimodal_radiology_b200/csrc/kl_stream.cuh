@@ -38,7 +38,8 @@ constexpr int kSubRows = 256;           // corpus rows per MMA (128 per CTA)
 constexpr int kSlots = 8;               // smem ring slots of 16 KB (256 rows x 64 B) per CTA
 constexpr int kSlotBytes = 256 * 64;
 constexpr int kMaxN = 256;              // queries per launch (MMA N)
-constexpr int kStreamThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1
+constexpr int kStreamThreads = 352;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1,
+                                        // warp 10 threshold refresher
 constexpr int kRefreshEvery = 64;       // appends of a query between threshold refresh attempts
 constexpr int kThrReload = 4;           // super-tiles between reloads of the published thresholds
 constexpr int kMinRows = 1 << 16;       // smaller corpora use the general path
@@ -167,12 +168,14 @@ struct StreamArgs {
     uint32_t* best_n;            // [n_pad]
     uint64_t* best;              // [n_pad][kCandCap] running best-k' list of every query (touched under the lock only)
     uint64_t* pool;              // [n_pad][pool_cap]
+    const uint16_t* klpack;      // raw table (bulk-copy experiment)
+    int dbg_bulk;                // RADAR_KLS_BULK: timing experiment, linear 16 KB bulk copies instead of TMA boxes (results invalid)
 };
 
 constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
                                     8 * 32 * 32 * sizeof(float) /*chunk staging*/ + 8 * kMaxN * sizeof(float) /*thresholds*/ +
-                                    kMaxN * sizeof(float) /*entropy*/ + 8 * kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
-                                    1024 /*barriers*/;
+                                    kMaxN * sizeof(float) /*entropy*/ + kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
+                                    1024 /*barriers + refresh requests*/;
 static_assert(kStreamSmemBytes <= 227 * 1024, "shared memory budget");
 
 // D[tmem] (+)= A[smem] * B[smem]^T, M = 256 across the CTA pair
@@ -249,14 +252,16 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     float* stage = reinterpret_cast<float*>(qtile + 128 * 64);                   // [8 warps][32 cols][32 lanes]
     float* thr_s = stage + 8 * 32 * 32;                                          // [8 warps][kMaxN] accumulator units
     float* h_s = thr_s + 8 * kMaxN;                                              // [kMaxN]
-    uint64_t* scratch = reinterpret_cast<uint64_t*>(h_s + kMaxN);                // [8 warps][kCandCap]
-    uint64_t* bars = scratch + 8 * kCandCap;
+    uint64_t* scratch = reinterpret_cast<uint64_t*>(h_s + kMaxN);                // [kCandCap] (refresher warp)
+    uint64_t* bars = scratch + kCandCap;
     uint64_t* full_bar = bars;                // [kSlots]
     uint64_t* empty_bar = full_bar + kSlots;  // [kSlots]
     uint64_t* tfull_bar = empty_bar + kSlots; // [8] one per accumulator stage PAIR
     uint64_t* tempty_bar = tfull_bar + 8;     // [8] 16 arrivals: 8 epilogue warps x 2 CTAs
     uint64_t* qfull_bar = tempty_bar + 8;     // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull_bar + 1);
+    uint32_t* refresh_req = tmem_slot + 2;    // [kMaxN / 32] bit per query: "fold my new entries, publish a threshold"
+    uint32_t* epi_done = refresh_req + kMaxN / 32;  // epilogue warps that have finished
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
@@ -279,6 +284,8 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         }
         mbar_init(qfull_bar, 1);
         fence_barrier_init();
+        for (int i = 0; i < kMaxN / 32; ++i) refresh_req[i] = 0u;
+        *epi_done = 0u;
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot);
     for (int i = threadIdx.x; i < N; i += kStreamThreads) h_s[i] = a.qshift[i];
@@ -302,7 +309,24 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         uint32_t slot = 0, sph = 0;
         for (int64_t t = unit; t < a.tiles; t += units) {
             mbar_wait(&empty_bar[slot], sph ^ 1);
-            if (elect_one()) {
+            if (a.dbg_bulk) {
+                if (elect_one()) {
+                    const int64_t r0 = min(t * kTileRows + static_cast<int64_t>(cta_rank) * 256, a.n - 256);
+                    if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes);
+                    if (leader)
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(ring + slot * kSlotBytes)),
+                            "l"(a.klpack + r0 * 32), "r"(kSlotBytes), "r"(smem_u32(&full_bar[slot]))
+                            : "memory");
+                    else
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                smem_u32(ring + slot * kSlotBytes)),
+                            "l"(a.klpack + r0 * 32), "r"(kSlotBytes), "r"(smem_u32(qfull_bar))
+                            : "memory");
+                }
+            } else if (elect_one()) {
                 if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes * 2);
                 tma_load_2d_pair(&map_kl, smem_u32(&full_bar[slot]), smem_u32(ring + slot * kSlotBytes), 0,
                                  static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 256);
@@ -349,6 +373,30 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 }
             }
         }
+    } else if (warp == 10) {
+        // ================================ threshold refresher ================================
+        // Folding pooled entries into a query's best-k' list takes microseconds; done by an epilogue warp it would hold
+        // up the accumulator hand-off of the whole CTA pair, so the epilogue warps only raise a request bit.
+        while (true) {
+            bool any = false;
+            for (int w = 0; w < N / 32; ++w) {
+                uint32_t bits = 0;
+                if (lane == 0) bits = atomicExch(&refresh_req[w], 0u);
+                bits = __shfl_sync(0xffffffffu, bits, 0);
+                any |= bits != 0u;
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    refresh_threshold(a, w * 32 + b, scratch, lane);
+                }
+            }
+            if (!any) {
+                uint32_t d = 0;
+                if (lane == 0) d = *reinterpret_cast<volatile uint32_t*>(epi_done);
+                if (__shfl_sync(0xffffffffu, d, 0) == 8u) break;
+                __nanosleep(200);
+            }
+        }
     } else {
         // ===================== epilogue warps: thread = corpus row; warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 ====
         const int quad = warp & 3;
@@ -358,7 +406,6 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         float* my_stage = stage + ew * 32 * 32 + lane;
         float* my_thr = thr_s + ew * kMaxN;
         const uint32_t my_thr_addr = smem_u32(my_thr);
-        uint64_t* my_scratch = scratch + ew * kCandCap;
         const int nq32 = N / 32;  // threshold words per lane
         // thresholds in accumulator units: key + H
         uint32_t pending[kMaxN / 32];
@@ -389,7 +436,6 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             mbar_wait(&tfull_bar[sp], aph);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>((sp * 2 + sub) * N);
-            int want_refresh = -1;
             for (int cb = 0; cb < nq32; ++cb) {
                 float v[32];
                 tmem_ld_x32(t_acc + cb * 32, v);
@@ -425,23 +471,19 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                         const uint32_t slot = atomicAdd(a.gcnt + qi, 1u);
                         if (slot < static_cast<uint32_t>(a.pool_cap))
                             a.pool[static_cast<int64_t>(qi) * a.pool_cap + slot] = make_composite(key, static_cast<uint32_t>(row));
-                        if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp)) want_refresh = qi;
+                        if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp))
+                            atomicOr(&refresh_req[qi >> 5], 1u << (qi & 31));
                     }
                     __syncwarp();
                 }
-            }
-            unsigned need = __ballot_sync(0xffffffffu, want_refresh >= 0);
-            while (need) {
-                const int src_lane = __ffs(need) - 1;
-                need &= need - 1;
-                const int qi = __shfl_sync(0xffffffffu, want_refresh, src_lane);
-                refresh_threshold(a, qi, my_scratch, lane);
             }
             if (++sp == static_cast<uint32_t>(spairs)) {
                 sp = 0;
                 aph ^= 1;
             }
         }
+        __syncwarp();
+        if (lane == 0) atomicAdd(epi_done, 1u);
     }
     tc_fence_before();
     __syncthreads();

@@ -180,13 +180,13 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->q_tiles = 1;
         pl->parts = 1;
         const int64_t qp = n_pad;
-        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * (5 * qp + 4), 256) + sizeof(uint64_t) * qp * pl->pool_cap;
-        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr | boot counter] then the pools
-        pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * (5 * qp + 4), 256);
+        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * (5 * qp + 8), 256) + sizeof(uint64_t) * qp * pl->pool_cap;
+        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr | boot counter | ucount] then the pools
+        pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * (5 * qp + 8), 256);
         pl->off_ks_best = carve(sizeof(uint64_t) * qp * kCandCap);
         pl->off_ks_tilemax = carve(sizeof(uint32_t) * qp * pl->sample_tiles);
         pl->off_qerr = carve(sizeof(float) * qp);
-        pl->off_ucount = carve(sizeof(uint32_t) * 4);
+        pl->off_ucount = pl->off_ks_zero + sizeof(uint32_t) * (5 * qp + 4);
         pl->off_ulist = carve(sizeof(uint32_t) * qp);
         pl->off_apack = carve(tc::apack_bytes(qp, RADAR_MODE_KL, c->d));
         const int64_t f_tiles = ceil_div64(q, kScanTQ);
@@ -229,8 +229,8 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
     if (algo == RADAR_ALGO_TC_FILTER) {
         pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
         if (p->precision == RADAR_PREC_FP32) {
-            // exact re-run of uncertified queries: sized for up to kFallbackMaxQ queries per pass
-            const int64_t fq = q < tc::kFallbackMaxQ ? q : tc::kFallbackMaxQ;
+            // exact re-run of uncertified queries: enqueued unconditionally with a device-side count, sized for all q
+            const int64_t fq = q;
             const int64_t f_tiles = ceil_div64(fq, kScanTQ);
             plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
             pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
@@ -268,6 +268,30 @@ static int launch_scan(const ScanArgs& a, int64_t q_tiles, cudaStream_t st) {
     if (a.mode == RADAR_MODE_DPR) simt_scan_kernel<true, false><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
     else if (a.mode == RADAR_MODE_KL) simt_scan_kernel<false, true><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
     else simt_scan_kernel<true, true><<<grid, kScanThreads, kScanSmemBytes, st>>>(a);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+// Exact re-run (canonical CUDA-core scan) of the queries listed in ulist[0 .. *ucount): enqueued unconditionally, the
+// kernels read the count on the device and exit at once when it is zero -- no host round trip inside a search call.
+static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_t* queries, int mode, int k, float alpha,
+                              float oma, int64_t q_max, const uint32_t* ucount, const uint32_t* ulist, int fb_parts,
+                              int64_t fb_rows_per_part, uint64_t* fb_cand, uint32_t* fb_cnt, uint64_t* fb_sel,
+                              float* out_scores, int64_t* out_idx, cudaStream_t st) {
+    ScanArgs a{};
+    a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
+    a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist; a.nq_dev = ucount;
+    a.nq = q_max; a.n = corpus->n; a.d = corpus->d; a.mode = mode; a.alpha = alpha; a.oma = oma;
+    a.parts = fb_parts; a.rows_per_part = fb_rows_per_part; a.kp = k; a.cand = fb_cand; a.cnt = fb_cnt;
+    int rc = launch_scan(a, ceil_div64(q_max, kScanTQ), st);
+    if (rc) return rc;
+    select_kernel<<<static_cast<unsigned>(ceil_div64(q_max, kSelWarps)), kSelWarps * 32, 0, st>>>(
+        fb_cand, fb_cnt, nullptr, q_max, ucount, fb_parts, kCandCap, k, fb_sel, nullptr);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    FinalArgs g{};
+    g.sel = fb_sel; g.R = k; g.k = k; g.mode = mode; g.sort = 0; g.qmap = ulist; g.nq_dev = ucount;
+    g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx;
+    final_kernel<<<static_cast<unsigned>(q_max), kFinalThreads, 0, st>>>(g);
     RADAR_CUDA_CHECK(cudaGetLastError());
     return RADAR_OK;
 }
@@ -403,6 +427,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
     const float oma = 1.0f - alpha;
     int launches = 0;
     int64_t uncertified = 0;
+    bool have_ucount = false;  // ucount holds the number of exactly re-run queries (read back only for statistics)
     unsigned long long* clk_dev = nullptr;
 
     if (pl.algo == RADAR_ALGO_KL_STREAM) {
@@ -417,7 +442,6 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         const size_t shift_off = align_up(sizeof(uint16_t) * static_cast<size_t>(qp) * RADAR_KLPACK, 256);
         float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(apack) + shift_off);
         RADAR_CUDA_CHECK(cudaMemsetAsync(zero, 0, pl.ks_zero_bytes, st));
-        RADAR_CUDA_CHECK(cudaMemsetAsync(ucount, 0, sizeof(uint32_t) * 4, st));
         tc::PackArgs pa{};
         pa.q_emb = nullptr; pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp;
         pa.d = corpus->d; pa.mode = RADAR_MODE_KL; pa.alpha = alpha; pa.oma = oma;
@@ -444,6 +468,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         sa.n = corpus->n; sa.tiles = pl.tiles; sa.q = static_cast<int>(q); sa.n_pad = pl.n_pad; sa.kp = pl.kp;
         sa.pool_cap = pl.pool_cap; sa.qshift = qshift; sa.gthr = gthr; sa.gcnt = gcnt; sa.lock = lock;
         sa.processed = processed; sa.best_n = best_n; sa.best = best; sa.pool = pool;
+        sa.klpack = corpus->klpack; sa.dbg_bulk = getenv("RADAR_KLS_BULK") ? 1 : 0;
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(kls::kl_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kls::kStreamSmemBytes)));
         int64_t units = pl.units;
@@ -472,32 +497,13 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(cudaGetLastError());
         launches += 4;
         // queries whose pool overflowed or (fp32 mode) whose certificate failed are re-run by the exact scan
-        uint32_t h_count = 0;
-        RADAR_CUDA_CHECK(cudaMemcpyAsync(&h_count, ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
-        uncertified = h_count;
-        if (h_count > 0) {
-            uint64_t* fb_cand = reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand);
-            uint32_t* fb_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt);
-            uint64_t* fb_sel = reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel);
-            const int64_t nb = h_count;
-            ScanArgs a{};
-            a.q_emb = nullptr; a.p16 = queries->p16; a.entropy = queries->entropy; a.c_emb = nullptr;
-            a.logq16 = corpus->logq16; a.qmap = ulist; a.nq = nb; a.n = corpus->n; a.d = corpus->d;
-            a.mode = RADAR_MODE_KL; a.alpha = alpha; a.oma = oma; a.parts = pl.fb_parts;
-            a.rows_per_part = pl.fb_rows_per_part; a.kp = params->k; a.cand = fb_cand; a.cnt = fb_cnt;
-            rc = launch_scan(a, ceil_div64(nb, kScanTQ), st);
-            if (rc) return rc;
-            select_kernel<<<static_cast<unsigned>(ceil_div64(nb, kSelWarps)), kSelWarps * 32, 0, st>>>(
-                fb_cand, fb_cnt, nullptr, nb, pl.fb_parts, kCandCap, params->k, fb_sel, nullptr);
-            RADAR_CUDA_CHECK(cudaGetLastError());
-            FinalArgs g{};
-            g.sel = fb_sel; g.R = params->k; g.k = params->k; g.mode = RADAR_MODE_KL; g.sort = 0; g.qmap = ulist;
-            g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx;
-            final_kernel<<<static_cast<unsigned>(nb), kFinalThreads, 0, st>>>(g);
-            RADAR_CUDA_CHECK(cudaGetLastError());
-            launches += 3;
-        }
+        rc = launch_exact_rerun(corpus, queries, RADAR_MODE_KL, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
+                                pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
+                                reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
+                                reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, st);
+        if (rc) return rc;
+        launches += 3;
+        have_ucount = true;
     } else if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
         ScanArgs a{};
         a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
@@ -510,7 +516,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
         ++launches;
         select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
-            cand, cnt, nullptr, q, pl.parts, kCandCap, pl.R, sel, nullptr);
+            cand, cnt, nullptr, q, nullptr, pl.parts, kCandCap, pl.R, sel, nullptr);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         FinalArgs f{};
@@ -537,7 +543,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         clk_dev = fl.clk_dev;
         launches += nl;
         select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
-            cand, cnt, thr, q, pl.parts, kCandCap, pl.R, sel, bound);
+            cand, cnt, thr, q, nullptr, pl.parts, kCandCap, pl.R, sel, bound);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         RescoreArgs r{};
@@ -559,40 +565,22 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         if (certify) {
-            // the only host round trip of a search call: 4 bytes, the number of queries to re-run exactly
+            rc = launch_exact_rerun(corpus, queries, params->mode, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
+                                    pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
+                                    reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
+                                    reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, st);
+            if (rc) return rc;
+            launches += 3;
+            have_ucount = true;
+        }
+    }
+    if (stats) {
+        if (have_ucount) {
             uint32_t h_count = 0;
             RADAR_CUDA_CHECK(cudaMemcpyAsync(&h_count, ucount, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
             uncertified = h_count;
-            uint64_t* fb_cand = reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand);
-            uint32_t* fb_cnt = reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt);
-            uint64_t* fb_sel = reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel);
-            for (int64_t done = 0; done < static_cast<int64_t>(h_count); done += tc::kFallbackMaxQ) {
-                const int64_t nb = (static_cast<int64_t>(h_count) - done) < tc::kFallbackMaxQ
-                                       ? (static_cast<int64_t>(h_count) - done)
-                                       : tc::kFallbackMaxQ;
-                ScanArgs a{};
-                a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
-                a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist + done;
-                a.nq = nb; a.n = corpus->n; a.d = corpus->d; a.mode = params->mode; a.alpha = alpha; a.oma = oma;
-                a.parts = pl.fb_parts; a.rows_per_part = pl.fb_rows_per_part; a.kp = params->k;
-                a.cand = fb_cand; a.cnt = fb_cnt;
-                rc = launch_scan(a, ceil_div64(nb, kScanTQ), st);
-                if (rc) return rc;
-                select_kernel<<<static_cast<unsigned>(ceil_div64(nb, kSelWarps)), kSelWarps * 32, 0, st>>>(
-                    fb_cand, fb_cnt, nullptr, nb, pl.fb_parts, kCandCap, params->k, fb_sel, nullptr);
-                RADAR_CUDA_CHECK(cudaGetLastError());
-                FinalArgs g{};
-                g.sel = fb_sel; g.R = params->k; g.k = params->k; g.mode = params->mode; g.sort = 0;
-                g.qmap = ulist + done; g.idx_offset = corpus->idx_offset; g.out_scores = out_scores;
-                g.out_idx = out_idx;
-                final_kernel<<<static_cast<unsigned>(nb), kFinalThreads, 0, st>>>(g);
-                RADAR_CUDA_CHECK(cudaGetLastError());
-                launches += 3;
-            }
         }
-    }
-    if (stats) {
         RADAR_CUDA_CHECK(cudaStreamSynchronize(st));
         stats->algo_used = pl.algo;
         stats->kernel_launches = launches;

@@ -31,7 +31,9 @@ struct ScanArgs {
     const float* c_emb;
     const float* logq16;
     const uint32_t* qmap;  // nullable: tile row -> query id (exact re-run of uncertified queries)
-    int64_t nq;            // tile rows in use
+    const uint32_t* nq_dev;  // nullable: DEVICE-side number of tile rows in use (<= nq); lets the re-run of uncertified
+                             // queries be enqueued without a host round trip -- CTAs beyond the count exit at once
+    int64_t nq;            // tile rows in use (upper bound when nq_dev is set)
     int64_t n;             // corpus rows
     int d;
     int mode;
@@ -126,12 +128,14 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
     const int ty = tid >> 4, tx = tid & 15;
     const int part = blockIdx.y;
     const int64_t q0 = static_cast<int64_t>(blockIdx.x) * kScanTQ;
+    const int64_t nq = a.nq_dev ? min(static_cast<int64_t>(*a.nq_dev), a.nq) : a.nq;
+    if (q0 >= nq) return;
     const int64_t part_begin = static_cast<int64_t>(part) * a.rows_per_part;
     const int64_t part_end = min(a.n, part_begin + a.rows_per_part);
 
     if (tid < kScanTQ) {
         const int64_t qi = q0 + tid;
-        const bool valid = qi < a.nq;
+        const bool valid = qi < nq;
         const uint32_t qid = valid ? (a.qmap ? a.qmap[qi] : static_cast<uint32_t>(qi)) : 0xFFFFFFFFu;
         qid_s[tid] = qid;
         thr[tid] = -CUDART_INF_F;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
         }
         __syncthreads();
     }
-    if (tid < kScanTQ && q0 + tid < a.nq) a.cnt[(q0 + tid) * a.parts + part] = cnt_s[tid];
+    if (tid < kScanTQ && q0 + tid < nq) a.cnt[(q0 + tid) * a.parts + part] = cnt_s[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -263,11 +267,13 @@ constexpr int kSelWarps = 8;  // queries per CTA (one warp each)
 __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* __restrict__ cand,
                                                                 const uint32_t* __restrict__ cnt,
                                                                 const float* __restrict__ thr_final, int64_t nq,
-                                                                int parts, int cap, int R, uint64_t* __restrict__ sel,
+                                                                const uint32_t* __restrict__ nq_dev, int parts, int cap,
+                                                                int R, uint64_t* __restrict__ sel,
                                                                 float* __restrict__ bound) {
     __shared__ uint64_t work[kSelWarps][kCandCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qi = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
+    if (nq_dev) nq = min(nq, static_cast<int64_t>(*nq_dev));
     if (qi >= nq) return;  // warp-uniform
     uint64_t* w = work[warp];
     float b = -CUDART_INF_F;
@@ -409,6 +415,7 @@ struct FinalArgs {
     int mode;
     int sort;  // 0: sel rows are already in final order
     const uint32_t* qmap;
+    const uint32_t* nq_dev;  // nullable: device-side number of queries (CTAs beyond it exit)
     int64_t idx_offset;
     float* out_scores;
     int64_t* out_idx;
@@ -426,6 +433,7 @@ __global__ void __launch_bounds__(kFinalThreads) final_kernel(const FinalArgs a)
     __shared__ uint64_t s[kFinalCap];
     const int64_t qi = blockIdx.x;
     const int tid = threadIdx.x;
+    if (a.nq_dev && qi >= static_cast<int64_t>(*a.nq_dev)) return;
     const int P = max(next_pow2(a.R), 2);
     for (int i = tid; i < P; i += kFinalThreads) s[i] = i < a.R ? a.sel[qi * a.R + i] : 0ull;
     if (a.sort) bitonic_sort_desc(s, P, tid, kFinalThreads, [] { __syncthreads(); });
