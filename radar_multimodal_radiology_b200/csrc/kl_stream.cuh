@@ -58,8 +58,7 @@ __host__ __device__ inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
     return static_cast<int>(s < boot_tiles ? s : boot_tiles);
 }
 
-// ---- boot: tile maxima of the canonical KL key over a strided sample of 256-row tiles; the last CTA to finish
-// turns them into the initial thresholds (k'-th largest tile maximum per query, lowered by the filter error bound)
+// ---- boot: tile maxima of the canonical KL key over a strided sample of 256-row tiles -----------------------------
 struct BootArgs {
     const float* logq16;   // [n][16]
     const float* p16;      // [q][16]
@@ -68,7 +67,6 @@ struct BootArgs {
     int64_t n, boot_tiles; // corpus rows, 256-row tiles
     int q, sample_tiles, kp;
     uint32_t* tilemax;     // [q][sample_tiles] ord-encoded keys (0 = no valid row)
-    uint32_t* done;        // CTA completion counter (zeroed before the launch)
     uint32_t* gthr;        // [q] out
 };
 
@@ -76,7 +74,6 @@ __global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a)
     __shared__ __align__(16) float ps[kMaxN * kObsPad];
     __shared__ float hs[kMaxN];
     __shared__ uint32_t wmax[kBootThreads / 32][kMaxN];
-    __shared__ uint32_t last_flag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q4 = (a.q + 3) & ~3;
     for (int i = tid; i < q4 * kObsPad; i += kBootThreads) ps[i] = i < a.q * kObsPad ? a.p16[i] : 0.0f;
@@ -126,33 +123,38 @@ __global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a)
         }
         __syncthreads();
     }
-    // ---- the last CTA computes the thresholds ----
-    __threadfence();
-    if (tid == 0) last_flag = atomicAdd(a.done, 1u) == gridDim.x - 1 ? 1u : 0u;
-    __syncthreads();
-    if (!last_flag) return;
-    __threadfence();
-    for (int qi = warp; qi < a.q; qi += kBootThreads / 32) {
-        const uint32_t* src = a.tilemax + static_cast<int64_t>(qi) * a.sample_tiles;
-        uint32_t val[kMaxSample / 32];
+}
+
+// k'-th largest tile maximum per query (one warp = one CTA per query, values in registers) -> initial threshold,
+// lowered by the filter error bound
+__global__ void __launch_bounds__(32) kl_boot_threshold_kernel(const BootArgs a) {
+    const int qi = blockIdx.x, lane = threadIdx.x;
+    const uint32_t* src = a.tilemax + static_cast<int64_t>(qi) * a.sample_tiles;
+    uint32_t val[kMaxSample / 32];
 #pragma unroll
-        for (int e = 0; e < kMaxSample / 32; ++e) {
-            const int i = lane + 32 * e;
-            val[e] = i < a.sample_tiles ? __ldcg(src + i) : 0u;
-        }
-        uint32_t key = 0;
-        if (a.sample_tiles >= a.kp) {
-#pragma unroll 1
-            for (int b = 31; b >= 0; --b) {
-                const uint32_t trial = key | (1u << b);
-                int c = 0;
-#pragma unroll
-                for (int e = 0; e < kMaxSample / 32; ++e) c += val[e] >= trial ? 1 : 0;
-                if (__reduce_add_sync(0xffffffffu, c) >= a.kp) key = trial;
-            }
-        }
-        if (lane == 0) a.gthr[qi] = key != 0u ? f2ord(__fsub_rn(ord2f(key), a.qerr[qi])) : 0u;  // 0 = no threshold
+    for (int e = 0; e < kMaxSample / 32; ++e) {
+        const int i = lane + 32 * e;
+        val[e] = i < a.sample_tiles ? src[i] : 0u;
     }
+    uint32_t key = 0;
+    if (a.sample_tiles >= a.kp) {
+#pragma unroll 1
+        for (int b = 30; b >= 0; b -= 2) {  // two bits per step: three independent counts, one dependent decision
+            const uint32_t t1 = key | (1u << b), t2 = key | (2u << b), t3 = key | (3u << b);
+            int c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+            for (int e = 0; e < kMaxSample / 32; ++e) {
+                c1 += val[e] >= t1 ? 1 : 0;
+                c2 += val[e] >= t2 ? 1 : 0;
+                c3 += val[e] >= t3 ? 1 : 0;
+            }
+            c1 = __reduce_add_sync(0xffffffffu, c1);
+            c2 = __reduce_add_sync(0xffffffffu, c2);
+            c3 = __reduce_add_sync(0xffffffffu, c3);
+            key = c3 >= a.kp ? t3 : (c2 >= a.kp ? t2 : (c1 >= a.kp ? t1 : key));
+        }
+    }
+    if (lane == 0) a.gthr[qi] = key != 0u ? f2ord(__fsub_rn(ord2f(key), a.qerr[qi])) : 0u;  // 0 = no threshold
 }
 
 // ---- stream -------------------------------------------------------------------------------------------------

@@ -452,9 +452,11 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         kls::BootArgs ba{};
         ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.qerr = qerr;
         ba.n = corpus->n; ba.boot_tiles = ceil_div64(corpus->n, kls::kBootRows); ba.q = static_cast<int>(q);
-        ba.sample_tiles = pl.sample_tiles; ba.kp = pl.kp; ba.tilemax = tilemax; ba.done = zero + 5 * qp; ba.gthr = gthr;
+        ba.sample_tiles = pl.sample_tiles; ba.kp = pl.kp; ba.tilemax = tilemax; ba.gthr = gthr;
         kls::kl_boot_kernel<<<static_cast<unsigned>(pl.sample_tiles < 4 * di.sms ? pl.sample_tiles : 4 * di.sms),
                               kls::kBootThreads, 0, st>>>(ba);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        kls::kl_boot_threshold_kernel<<<static_cast<unsigned>(q), 32, 0, st>>>(ba);
         RADAR_CUDA_CHECK(cudaGetLastError());
         CUtensorMap map_kl, map_q;
         memset(&map_kl, 0, sizeof map_kl);
@@ -495,7 +497,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         fa.out_scores = out_scores; fa.out_idx = out_idx; fa.uncert_count = ucount; fa.uncert_list = ulist;
         kls::kl_stream_final_kernel<<<static_cast<unsigned>(q), kls::kFinThreads, 0, st>>>(fa);
         RADAR_CUDA_CHECK(cudaGetLastError());
-        launches += 4;
+        launches += 5;
         // queries whose pool overflowed or (fp32 mode) whose certificate failed are re-run by the exact scan
         rc = launch_exact_rerun(corpus, queries, RADAR_MODE_KL, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
                                 pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),

@@ -315,6 +315,36 @@ class GpuIndexFlatIP(RadarIndex):
         return dev_s, dev_i
 
 
+class GraphedSearch:
+    """A fixed-shape ``search`` call captured once in a CUDA graph and replayed.
+
+    A search is a short chain of kernel launches (query preparation, the fused score + top-k kernel, select /
+    re-score / final, and for a sharded index the all-gather + merge); for small batches the launch latency of
+    that chain is comparable to the kernels themselves.  ``replay()`` re-runs the captured chain on the SAME input
+    tensors (copy new queries into them first) and returns the same output tensors.  ``index`` is a
+    :class:`RadarIndex` or a ``ShardedRadarIndex``; keyword arguments are those of ``search``.
+    """
+
+    def __init__(self, index, x, k: int, warmup: int = 2, **search_kw):
+        dev = index.device
+        search_kw.pop("collect_stats", None)  # statistics need a stream sync, which a capture cannot contain
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: workspace allocation, driver entry points
+            for _ in range(max(1, warmup)):
+                index.search(x, k, **search_kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = index.search(x, k, **search_kw)
+        self.index = index
+
+    def replay(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        self.graph.replay()
+        return self.out
+
+
 def merge_topk(scores: torch.Tensor, ids: torch.Tensor, k: int, ascending: bool
                ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k of the union of per-shard lists; ``scores``/``ids`` are [parts, Q, k_in] CUDA tensors (the
