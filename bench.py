@@ -324,7 +324,11 @@ def main():
     # ---- the same search chain captured once per round in a CUDA graph (GraphedSearch); eager launches remain the
     # fallback and are what the statistics / kernel-event passes use
     graphed, graph_note = None, "eager"
-    if not args.no_graph:
+    if world > 1:
+        # a graph that captured NCCL collectives keeps the communicator busy at teardown (destroy_process_group hung
+        # for minutes on this stack), and with >= 15 ms of kernel per step the launch chain is hidden anyway
+        graph_note = "eager (collectives are not captured in a graph)"
+    elif not args.no_graph:
         try:
             from radar_multimodal_radiology_b200.index import GraphedSearch
             graphed = [GraphedSearch(index, q_emb, k, query_probs=q_pr, mask=masks[r], alpha=ALPHA, mode=mode)
@@ -476,6 +480,8 @@ def main():
                              "filter_sm_mhz": round(stats.filter_sm_mhz, 1)},
         }
         print(json.dumps(line), flush=True)
+    graphed = None
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
