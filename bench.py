@@ -483,8 +483,13 @@ def main():
     graphed = None
     torch.cuda.synchronize()
     if world > 1:
+        # the JSON line is out; a communicator teardown that stalls must not hold the launcher hostage
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.barrier()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":
