@@ -151,6 +151,49 @@ class RadarIndex:
         self.emb_f32 = self.emb_bf16 = self.logq16 = self.klpack = None
         self.emb_max_norm = 0.0
 
+    # ---- persistence (the reference rebuilds its index in RAM on every run) ----------
+    def save(self, path: str) -> None:
+        """Write this (shard of the) index as ``<path>.safetensors`` + ``<path>.json``.
+
+        The reference persists model weights with safetensors (train_expert_models.py:279-283) and never persists the
+        retrieval index (dpr.py:278-303); here the resident tensors are stored as they sit in HBM -- canonical fp32
+        embeddings, their bf16 copy, the fp32 log table and its bf16 [hi|lo] pack -- so loading is a plain copy."""
+        import json
+        from safetensors.torch import save_file
+        tensors = {}
+        for name in ("emb_f32", "emb_bf16", "logq16", "klpack"):
+            t = getattr(self, name)
+            if t is not None:
+                tensors[name] = t.detach().cpu().contiguous()
+        save_file(tensors, path + ".safetensors")
+        meta = dict(format="radar-index-v1", d=self.d, ntotal=self.ntotal, eps=self.eps, normalize=self.normalize,
+                    idx_offset=self.idx_offset, emb_max_norm=self.emb_max_norm, precision=self.precision,
+                    tensors=sorted(tensors))
+        with open(path + ".json", "w") as fh:
+            json.dump(meta, fh, indent=1)
+
+    @classmethod
+    def load(cls, path: str, device: Union[str, torch.device] = "cuda", **kw) -> "RadarIndex":
+        """Inverse of :meth:`save`; ``kw`` overrides constructor arguments such as ``precision`` / ``algo``."""
+        import json
+        from safetensors.torch import load_file
+        with open(path + ".json") as fh:
+            meta = json.load(fh)
+        if meta.get("format") != "radar-index-v1":
+            raise ValueError(f"{path}.json is not a radar index (format={meta.get('format')!r})")
+        args = dict(d=meta["d"], device=device, precision=meta["precision"], eps=meta["eps"],
+                    normalize=meta["normalize"], idx_offset=meta["idx_offset"])
+        args.update(kw)
+        index = cls(**args)
+        tensors = load_file(path + ".safetensors", device=str(index.device))
+        for name in ("emb_f32", "emb_bf16", "logq16", "klpack"):
+            if name in tensors:
+                setattr(index, name, tensors[name].contiguous())
+        index.emb_max_norm = float(meta["emb_max_norm"])
+        if index.ntotal != meta["ntotal"]:
+            raise ValueError(f"{path}: expected {meta['ntotal']} rows, found {index.ntotal}")
+        return index
+
     # ---- search -------------------------------------------------------------------------------------
     def _corpus_struct(self, mode: int) -> L.CorpusStruct:
         c = L.CorpusStruct()

@@ -218,3 +218,27 @@ def test_shard_bounds_cover_the_corpus():
         assert bounds == ro.shard_bounds(n, w)
         assert bounds[0][0] == 0 and bounds[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:]))
+
+
+def test_batched_retrieval_metrics_match_reference_fixtures(ref_fixtures):
+    """RetrievalMetrics (evaluate_retrieval_system.py:137-188) for a whole batch at once == the per-query values the
+    reference itself produced (tests/golden/make_reference_fixtures.py)."""
+    import torch
+    from radar_multimodal_radiology_b200.metrics import batched_retrieval_metrics
+    cases = ref_fixtures["retrieval_metrics"]
+    kmax = max(len(c["retrieved"]) for c in cases)
+    rmax = max(1, max(len(c["relevant"]) for c in cases))
+    ids = torch.full((len(cases), kmax), -1, dtype=torch.int64)
+    rel = torch.full((len(cases), rmax), -1, dtype=torch.int64)
+    for i, c in enumerate(cases):
+        ids[i, :len(c["retrieved"])] = torch.tensor(c["retrieved"], dtype=torch.int64)
+        if c["relevant"]:
+            rel[i, :len(c["relevant"])] = torch.tensor(c["relevant"], dtype=torch.int64)
+    got = batched_retrieval_metrics(ids, rel)
+    checked = 0
+    for name, values in got.items():
+        for i, c in enumerate(cases):
+            if name in c:  # the reference fixture holds the metrics its evaluators report
+                assert abs(float(values[i]) - c[name]) < 1e-12, (name, i, float(values[i]), c[name])
+                checked += 1
+    assert checked >= 10 * len(cases)
