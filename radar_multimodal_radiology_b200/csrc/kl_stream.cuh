@@ -170,8 +170,6 @@ struct StreamArgs {
     uint32_t* best_n;            // [n_pad]
     uint64_t* best;              // [n_pad][kCandCap] running best-k' list of every query (touched under the lock only)
     uint64_t* pool;              // [n_pad][pool_cap]
-    const uint16_t* klpack;      // raw table (bulk-copy experiment)
-    int dbg_bulk;                // RADAR_KLS_BULK: timing experiment, linear 16 KB bulk copies instead of TMA boxes (results invalid)
 };
 
 constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
@@ -311,24 +309,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         uint32_t slot = 0, sph = 0;
         for (int64_t t = unit; t < a.tiles; t += units) {
             mbar_wait(&empty_bar[slot], sph ^ 1);
-            if (a.dbg_bulk) {
-                if (elect_one()) {
-                    const int64_t r0 = min(t * kTileRows + static_cast<int64_t>(cta_rank) * 256, a.n - 256);
-                    if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes);
-                    if (leader)
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                smem_u32(ring + slot * kSlotBytes)),
-                            "l"(a.klpack + r0 * 32), "r"(kSlotBytes), "r"(smem_u32(&full_bar[slot]))
-                            : "memory");
-                    else
-                        asm volatile(
-                            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                smem_u32(ring + slot * kSlotBytes)),
-                            "l"(a.klpack + r0 * 32), "r"(kSlotBytes), "r"(smem_u32(qfull_bar))
-                            : "memory");
-                }
-            } else if (elect_one()) {
+            if (elect_one()) {
                 if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes * 2);
                 tma_load_2d_pair(&map_kl, smem_u32(&full_bar[slot]), smem_u32(ring + slot * kSlotBytes), 0,
                                  static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 256);
