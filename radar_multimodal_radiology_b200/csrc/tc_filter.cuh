@@ -38,7 +38,6 @@ namespace tc {
 
 constexpr int kBlockM = 128;          // query rows per CTA == TMEM lanes
 constexpr int kTileQ = 2 * kBlockM;   // query rows per work tile (CTA pair)
-constexpr int kFallbackMaxQ = 4096;   // uncertified queries re-run per exact pass
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 constexpr int kTmemCols = 512;
 constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
