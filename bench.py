@@ -443,7 +443,14 @@ def main():
     else:
         roof = {"bound": "tensor", "achieved": flops / (kern_ms_avg * 1e-3) / 1e12, "peak": tc_peak, "unit": "TFLOP/s"}
     roof["frac"] = roof["achieved"] / roof["peak"]
-    roof["traffic"] = None
+    roof["traffic"] = None  # DRAM bytes of this kernel per launch from the committed ncu capture of the same workload
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        if tr and world == 1 and not (args.n or args.q or args.k):
+            roof["traffic"] = tr["bytes"]
+            roof["traffic_source"] = tr["source"]
+    except (OSError, ValueError):
+        pass
     roof["kernel"] = "tc_filter_kernel" if stats.algo_used == 2 else "simt_scan_kernel"
     roof["kernel_ms"] = kern_ms_avg
     roof["peak_source"] = peak_src + (", sustained" if kern_ms_avg > 50 and roof["bound"] == "tensor" else ", burst")
