@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RADAR_ABI_VERSION 1
+#define RADAR_ABI_VERSION 2
 
 #define RADAR_NUM_OBS 14 /* CheXpert-14, train_expert_models.py:50-65 */
 #define RADAR_OBS_PAD 16 /* K=16 padded contraction */
@@ -85,6 +85,9 @@ typedef struct radar_corpus {
     float emb_max_norm;       /* max_n ||emb_f32[n]||_2 (host value; from radar_pack_embeddings) */
     float logq_max_abs;       /* max |logq16| (host value; <= |log eps|) */
     int64_t idx_offset;       /* added to every returned id (global id of row 0 of this shard) */
+    float logq_col_max[RADAR_OBS_PAD]; /* per observation j: max_n |logq16[n][j]| (host values); all zero => logq_max_abs
+                                          is used for every column.  Only tightens the filter's error bound (fewer exact
+                                          re-runs in FP32 mode, tighter initial thresholds on the KL stream path). */
 } radar_corpus_t;
 
 /* Query batch.  Pointers a mode does not need may be NULL. */

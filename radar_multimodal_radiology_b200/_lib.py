@@ -36,6 +36,7 @@ class CorpusStruct(C.Structure):
         ("n", C.c_int64), ("d", C.c_int32), ("reserved0", C.c_int32),
         ("emb_f32", C.c_void_p), ("emb_bf16", C.c_void_p), ("logq16", C.c_void_p), ("klpack", C.c_void_p),
         ("emb_max_norm", C.c_float), ("logq_max_abs", C.c_float), ("idx_offset", C.c_int64),
+        ("logq_col_max", C.c_float * 16),
     ]
 
 

@@ -446,6 +446,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         pa.q_emb = nullptr; pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp;
         pa.d = corpus->d; pa.mode = RADAR_MODE_KL; pa.alpha = alpha; pa.oma = oma;
         pa.emb_max_norm = corpus->emb_max_norm; pa.logq_max_abs = corpus->logq_max_abs;
+        tc::fill_col_max(corpus, pa.logq_col_max);
         pa.apack = apack; pa.qshift = qshift; pa.qerr = qerr;
         tc::query_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
         RADAR_CUDA_CHECK(cudaGetLastError());

@@ -191,6 +191,7 @@ struct PackArgs {
     int d, mode;
     float alpha, oma;
     float emb_max_norm, logq_max_abs;
+    float logq_col_max[kObsPad];  // per-observation max |log q| over the corpus (all zero: use logq_max_abs)
     uint16_t* apack;
     float* qshift;  // [q_pad]
     float* qerr;    // [q_pad]
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) query_pack_kernel(const PackArgs a) {
             const __nv_bfloat16 lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
             dst[(has_ip ? a.d : 0) + lane] = hi;
             dst[(has_ip ? a.d : 0) + kObsPad + lane] = lo;
-            sv = fabsf(v);
+            sv = fabsf(v) * a.logq_col_max[lane];  // sum_j |v_j| max_n |L_nj| >= sum_j |v_j L_nj| for every case n
         }
         for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
     }
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256) query_pack_kernel(const PackArgs a) {
         //   with the lo*lo product dropped: (2^-17 + 2^-18) sum|v||L| ; canonical combine / shift roundings:
         //   2^-20 of the magnitudes involved.
         const float ip_mag = sqrtf(ss) * a.emb_max_norm;
-        const float kl_mag = sv * a.logq_max_abs;
+        const float kl_mag = sv;
         const float e = 0.00403f * ip_mag + 1.65e-4f * kl_mag + 1e-6f * (fabsf(shift) + ip_mag + kl_mag) + 1e-30f;
         a.qshift[row] = shift;
         a.qerr[row] = e;
@@ -788,6 +789,13 @@ static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cuda
     return RADAR_OK;
 }
 
+// per-observation bound on |log q|: the caller's column maxima when given (any non-zero entry), else logq_max_abs
+static inline void fill_col_max(const radar_corpus_t* c, float* out) {
+    bool given = false;
+    for (int j = 0; j < kObsPad; ++j) given |= c->logq_col_max[j] > 0.0f;
+    for (int j = 0; j < kObsPad; ++j) out[j] = given ? c->logq_col_max[j] * 1.0001f : c->logq_max_abs;
+}
+
 // apack region layout: [q_pad * a_cols] uint16, then (256-byte aligned) qshift [q_pad] floats
 static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
     size_t b = sizeof(uint16_t) * static_cast<size_t>(q_pad) * a_cols_for(mode, d);
@@ -804,6 +812,7 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     pa.q_emb = fl.queries->emb_f32; pa.p16 = fl.queries->p16; pa.entropy = fl.queries->entropy;
     pa.q = fl.q; pa.q_pad = q_pad; pa.d = fl.corpus->d; pa.mode = fl.mode; pa.alpha = fl.alpha; pa.oma = fl.oma;
     pa.emb_max_norm = fl.corpus->emb_max_norm; pa.logq_max_abs = fl.corpus->logq_max_abs;
+    fill_col_max(fl.corpus, pa.logq_col_max);
     pa.apack = fl.apack; pa.qshift = qshift; pa.qerr = fl.qerr;
     query_pack_kernel<<<static_cast<unsigned>((q_pad * 32 + 255) / 256), 256, 0, st>>>(pa);
     RADAR_CUDA_CHECK(cudaGetLastError());

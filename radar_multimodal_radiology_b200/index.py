@@ -94,6 +94,7 @@ class RadarIndex:
         self.logq16: Optional[torch.Tensor] = None
         self.klpack: Optional[torch.Tensor] = None
         self.emb_max_norm = 0.0
+        self.logq_col_max = [0.0] * L.OBS_PAD  # per observation: max |log q| over the rows added so far
         self._workspace: Optional[torch.Tensor] = None
         self.last_stats = SearchStats()
         L.lib()  # fail loudly now if the extension is missing
@@ -144,12 +145,15 @@ class RadarIndex:
         L.check(L.lib().radar_kl_prepare_corpus(L.ptr(p), n, L.NUM_OBS, self.eps, int(self.normalize), L.ptr(logq),
                                                 L.ptr(pack), L.current_stream_ptr(self.device)),
                 "radar_kl_prepare_corpus")
+        col = logq.abs().amax(dim=0).tolist()  # one sync per add; tightens the filter's error bound
+        self.logq_col_max = [max(a, float(b)) for a, b in zip(self.logq_col_max, col)]
         self.logq16 = logq if self.logq16 is None else torch.cat([self.logq16, logq], 0)
         self.klpack = pack if self.klpack is None else torch.cat([self.klpack, pack], 0)
 
     def reset(self) -> None:
         self.emb_f32 = self.emb_bf16 = self.logq16 = self.klpack = None
         self.emb_max_norm = 0.0
+        self.logq_col_max = [0.0] * L.OBS_PAD
 
     # ---- persistence (the reference rebuilds its index in RAM on every run) ----------
     def save(self, path: str) -> None:
@@ -168,7 +172,7 @@ class RadarIndex:
         save_file(tensors, path + ".safetensors")
         meta = dict(format="radar-index-v1", d=self.d, ntotal=self.ntotal, eps=self.eps, normalize=self.normalize,
                     idx_offset=self.idx_offset, emb_max_norm=self.emb_max_norm, precision=self.precision,
-                    tensors=sorted(tensors))
+                    logq_col_max=self.logq_col_max, tensors=sorted(tensors))
         with open(path + ".json", "w") as fh:
             json.dump(meta, fh, indent=1)
 
@@ -190,6 +194,7 @@ class RadarIndex:
             if name in tensors:
                 setattr(index, name, tensors[name].contiguous())
         index.emb_max_norm = float(meta["emb_max_norm"])
+        index.logq_col_max = [float(v) for v in meta.get("logq_col_max", [0.0] * L.OBS_PAD)]
         if index.ntotal != meta["ntotal"]:
             raise ValueError(f"{path}: expected {meta['ntotal']} rows, found {index.ntotal}")
         return index
@@ -214,6 +219,8 @@ class RadarIndex:
         c.emb_max_norm = self.emb_max_norm
         c.logq_max_abs = abs(math.log(self.eps)) * 1.0001
         c.idx_offset = self.idx_offset
+        for j in range(L.OBS_PAD):
+            c.logq_col_max[j] = self.logq_col_max[j] if mode != L.MODE_DPR else 0.0
         return c
 
     def _get_workspace(self, nbytes: int) -> torch.Tensor:

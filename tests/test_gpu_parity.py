@@ -596,7 +596,7 @@ def test_config4_hybrid_10m_cases_top32_shards_and_exact_scan(dev):
             sh = RadarIndex(512, device=dev, precision="bf16", idx_offset=lo)
             sh.emb_f32, sh.emb_bf16 = idx.emb_f32[lo:hi], idx.emb_bf16[lo:hi]
             sh.logq16, sh.klpack = idx.logq16[lo:hi], idx.klpack[lo:hi]
-            sh.emb_max_norm = idx.emb_max_norm
+            sh.emb_max_norm, sh.logq_col_max = idx.emb_max_norm, idx.logq_col_max
             s, i = sh.search(q_emb[sub], k, precision="fp32", **kw_sub)
             ss.append(s)
             ii.append(i)

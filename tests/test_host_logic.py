@@ -19,7 +19,7 @@ def test_abi_library_loads_and_exports_every_declared_symbol(built_lib):
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), f"{name} not exported"
-    assert built_lib.radar_abi_version() == 1
+    assert built_lib.radar_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (radar_[a-z0-9_]+)", out))
     assert declared <= exported
