@@ -38,7 +38,7 @@ constexpr int kSubRows = 256;           // corpus rows per MMA (128 per CTA)
 constexpr int kSlots = 8;               // smem ring slots of 16 KB (256 rows x 64 B) per CTA
 constexpr int kSlotBytes = 256 * 64;
 constexpr int kMaxN = 256;              // queries per launch (MMA N)
-constexpr int kStreamThreads = 352;     // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1,
+constexpr int kStreamThreads = 352;     // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue sets (alternating super-tiles),
                                         // warp 10 threshold refresher
 constexpr int kRefreshEvery = 64;       // appends of a query between threshold refresh attempts
 constexpr int kThrReload = 4;           // super-tiles between reloads of the published thresholds
@@ -257,7 +257,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     uint64_t* full_bar = bars;                // [kSlots]
     uint64_t* empty_bar = full_bar + kSlots;  // [kSlots]
     uint64_t* tfull_bar = empty_bar + kSlots; // [8] one per accumulator stage PAIR
-    uint64_t* tempty_bar = tfull_bar + 8;     // [8] 16 arrivals: 8 epilogue warps x 2 CTAs
+    uint64_t* tempty_bar = tfull_bar + 8;     // [8] 8 arrivals: the 4 warps of one epilogue set x 2 CTAs
     uint64_t* qfull_bar = tempty_bar + 8;     // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull_bar + 1);
     uint32_t* refresh_req = tmem_slot + 2;    // [kMaxN / 32] bit per query: "fold my new entries, publish a threshold"
@@ -280,7 +280,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         }
         for (int i = 0; i < 8; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 16);
+            mbar_init(&tempty_bar[i], 8);
         }
         mbar_init(qfull_bar, 1);
         fence_barrier_init();
@@ -381,10 +381,13 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             }
         }
     } else {
-        // ===================== epilogue warps: thread = corpus row; warps 2-5 take sub-tile 0, warps 6-9 sub-tile 1 ====
+        // ===================== epilogue warps: thread = corpus row ====================================================
+        // Two sets of four warps (2-5 and 6-9, one warp per TMEM lane quadrant) alternate over the super-tiles of the
+        // pair; a warp reads BOTH M = 256 sub-tiles of its super-tile (two back-to-back tcgen05.ld per 32 queries), so
+        // one barrier round trip and one threshold fetch serve 2 x 32 cases per lane quadrant.
         const int quad = warp & 3;
         const int ew = warp - 2;           // 0..7
-        const int sub = ew >> 2;           // MMA sub-tile of the super-tile this warp reads
+        const int set = ew >> 2;           // which super-tiles (local index parity) this warp takes
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         float* my_stage = stage + ew * 32 * 32 + lane;
         float* my_thr = thr_s + ew * kMaxN;
@@ -405,64 +408,76 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             }
             __syncwarp();
         };
+        // rare path of one 32-case x 32-query chunk held in registers: stage it, walk the survivor bits
+        auto append_survivors = [&](const float (&v)[32], int cb, int64_t row, bool row_ok) {
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                my_stage[c * 32] = v[c];
+                mask |= (v[c] >= my_thr[cb * 32 + c] ? 1u : 0u) << c;
+            }
+            if (!row_ok) mask = 0;
+            while (mask) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const int qi = cb * 32 + c;
+                const float key = __fsub_rn(my_stage[c * 32], h_s[qi]);
+                const uint32_t slot = atomicAdd(a.gcnt + qi, 1u);
+                if (slot < static_cast<uint32_t>(a.pool_cap))
+                    a.pool[static_cast<int64_t>(qi) * a.pool_cap + slot] = make_composite(key, static_cast<uint32_t>(row));
+                if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp))
+                    atomicOr(&refresh_req[qi >> 5], 1u << (qi & 31));
+            }
+            __syncwarp();
+        };
         commit_thresholds();
-        uint32_t sp = 0, aph = 0, since = 0;
-        for (int64_t t = unit; t < a.tiles; t += units) {
-            if (++since == kThrReload) {  // use the values requested kThrReload super-tiles ago, request fresh ones
+        uint32_t since = 0, j = 0;
+        for (int64_t t = unit; t < a.tiles; t += units, ++j) {
+            // a waiter must see every phase of its barriers: with an even number of stage pairs a set meets each of "its"
+            // stage pairs on every use; with a single stage pair (N = 256) set 0 takes every super-tile
+            if (spairs > 1 ? (j & 1u) != static_cast<uint32_t>(set) : set != 0) continue;
+            const uint32_t sp = j % static_cast<uint32_t>(spairs), aph = (j / static_cast<uint32_t>(spairs)) & 1u;
+            if (++since == kThrReload / 2) {  // use the values requested a few super-tiles ago, request fresh ones
                 since = 0;
                 commit_thresholds();
 #pragma unroll
                 for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
             }
-            const int64_t row = t * kTileRows + static_cast<int64_t>(cta_rank) * 256 + sub * 128 + quad * 32 + lane;
-            const bool row_ok = row < a.n;
+            const int64_t row0 = t * kTileRows + static_cast<int64_t>(cta_rank) * 256 + quad * 32 + lane;
+            const int64_t row1 = row0 + 128;
+            const bool ok0 = row0 < a.n, ok1 = row1 < a.n;
             mbar_wait(&tfull_bar[sp], aph);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>((sp * 2 + sub) * N);
+            const uint32_t t_acc = tmem_base + lane_addr + static_cast<uint32_t>(sp * 2 * N);
             for (int cb = 0; cb < nq32; ++cb) {
-                float v[32];
-                tmem_ld_x32(t_acc + cb * 32, v);
+                float v0[32], v1[32];
+                tmem_ld_x32(t_acc + cb * 32, v0);
+                tmem_ld_x32(t_acc + N + cb * 32, v1);
                 tmem_wait_ld();
-                if (cb == nq32 - 1) {  // the accumulator stage is free again once its last columns are in registers
+                if (cb == nq32 - 1) {  // both accumulator stages are free again once their last columns are in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&tempty_bar[sp]);
                 }
-                bool h0 = false, h1 = false, h2 = false, h3 = false;  // four independent predicate chains
+                bool g0 = false, g1 = false, g2 = false, g3 = false;  // independent predicate chains, sub-tile 0
+                bool h0 = false, h1 = false, h2 = false, h3 = false;  // sub-tile 1
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
                     const float4 th = lds_f4(my_thr_addr + (cb * 32 + 4 * c4) * 4);  // broadcast
-                    h0 |= v[4 * c4 + 0] >= th.x;
-                    h1 |= v[4 * c4 + 1] >= th.y;
-                    h2 |= v[4 * c4 + 2] >= th.z;
-                    h3 |= v[4 * c4 + 3] >= th.w;
+                    g0 |= v0[4 * c4 + 0] >= th.x;
+                    g1 |= v0[4 * c4 + 1] >= th.y;
+                    g2 |= v0[4 * c4 + 2] >= th.z;
+                    g3 |= v0[4 * c4 + 3] >= th.w;
+                    h0 |= v1[4 * c4 + 0] >= th.x;
+                    h1 |= v1[4 * c4 + 1] >= th.y;
+                    h2 |= v1[4 * c4 + 2] >= th.z;
+                    h3 |= v1[4 * c4 + 3] >= th.w;
                 }
-                const bool hit = (h0 | h1 | h2 | h3) && row_ok;
-                if (__any_sync(0xffffffffu, hit)) {
-                    uint32_t mask = 0;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        my_stage[c * 32] = v[c];
-                        mask |= (v[c] >= my_thr[cb * 32 + c] ? 1u : 0u) << c;
-                    }
-                    if (!row_ok) mask = 0;
-                    while (mask) {
-                        const int c = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int qi = cb * 32 + c;
-                        const float key = __fsub_rn(my_stage[c * 32], h_s[qi]);
-                        const uint32_t slot = atomicAdd(a.gcnt + qi, 1u);
-                        if (slot < static_cast<uint32_t>(a.pool_cap))
-                            a.pool[static_cast<int64_t>(qi) * a.pool_cap + slot] = make_composite(key, static_cast<uint32_t>(row));
-                        if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp))
-                            atomicOr(&refresh_req[qi >> 5], 1u << (qi & 31));
-                    }
-                    __syncwarp();
+                const bool hit0 = (g0 | g1 | g2 | g3) && ok0, hit1 = (h0 | h1 | h2 | h3) && ok1;
+                if (__any_sync(0xffffffffu, hit0 | hit1)) {
+                    if (__any_sync(0xffffffffu, hit0)) append_survivors(v0, cb, row0, ok0);
+                    if (__any_sync(0xffffffffu, hit1)) append_survivors(v1, cb, row1, ok1);
                 }
-            }
-            if (++sp == static_cast<uint32_t>(spairs)) {
-                sp = 0;
-                aph ^= 1;
             }
         }
         __syncwarp();
