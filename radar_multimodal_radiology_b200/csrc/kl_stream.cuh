@@ -431,13 +431,17 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             __syncwarp();
         };
         commit_thresholds();
-        uint32_t since = 0, j = 0;
-        for (int64_t t = unit; t < a.tiles; t += units, ++j) {
-            // a waiter must see every phase of its barriers: with an even number of stage pairs a set meets each of "its"
-            // stage pairs on every use; with a single stage pair (N = 256) set 0 takes every super-tile
-            if (spairs > 1 ? (j & 1u) != static_cast<uint32_t>(set) : set != 0) continue;
-            const uint32_t sp = j % static_cast<uint32_t>(spairs), aph = (j / static_cast<uint32_t>(spairs)) & 1u;
-            if (++since == kThrReload / 2) {  // use the values requested a few super-tiles ago, request fresh ones
+        // A waiter must see every phase of its barriers: with an even number of stage pairs (a power of two) a set meets
+        // each of "its" stage pairs on every use; with a single stage pair (N = 256) set 0 takes every super-tile.
+        const uint32_t jstep = spairs > 1 ? 2u : 1u;
+        const uint32_t sp_mask = static_cast<uint32_t>(spairs) - 1u, sp_shift = 31u - __clz(static_cast<uint32_t>(spairs));
+        const bool idle = spairs == 1 && set != 0;
+        uint32_t since = 0;
+        for (uint32_t j = spairs > 1 ? static_cast<uint32_t>(set) : 0u; !idle; j += jstep) {
+            const int64_t t = unit + static_cast<int64_t>(j) * units;
+            if (t >= a.tiles) break;
+            const uint32_t sp = j & sp_mask, aph = (j >> sp_shift) & 1u;
+            if (++since == kThrReload) {  // use the values requested a few super-tiles ago, request fresh ones
                 since = 0;
                 commit_thresholds();
 #pragma unroll
