@@ -63,6 +63,8 @@ struct Plan {
     int64_t rows_per_part;
     // workspace offsets (bytes)
     size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
+    size_t off_groupmax;  // KL threshold prepass
+    int groups, group_tiles, tile_stride, groups_per_slab;
     size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
     // KL stream path
     int n_pad, pool_cap, sample_tiles;
@@ -228,6 +230,27 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
     pl->off_ulist = carve(sizeof(uint32_t) * q);
     if (algo == RADAR_ALGO_TC_FILTER) {
         pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
+        // KL with many queries over a small corpus: the cold-start survivors (~k' ln n per query) cost more than a second
+        // sweep of the (cheap) KL contraction, so a prepass collects group maxima and the real pass starts from
+        // near-exact thresholds.  Groups: about 384 per query, at least 4 k'.
+        if (p->mode == RADAR_MODE_KL && c->n <= (2ll << 20) && pl->q_tiles >= 8) {
+            const int64_t c_tiles = ceil_div64(c->n, tc::block_n_for_mode(RADAR_MODE_KL));
+            int64_t stride = c_tiles / 768;  // the prepass visits ~768-1500 sampled tiles per slab sweep
+            if (stride < 1) stride = 1;
+            // groups are formed per slab (a slab's sampled tiles are numbered from the slab start), so bound them per slab
+            const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, tc::block_n_for_mode(RADAR_MODE_KL)), stride);
+            int64_t gt = ceil_div64(slab_tiles * pl->parts, 384);
+            if (gt < 1) gt = 1;
+            const int64_t groups_per_slab = ceil_div64(slab_tiles, gt);
+            const int64_t groups = groups_per_slab * pl->parts;
+            if (groups >= 4 * pl->kp && groups <= 32 * tc::kMaxGroups32) {
+                pl->groups = static_cast<int>(groups);
+                pl->group_tiles = static_cast<int>(gt);
+                pl->tile_stride = static_cast<int>(stride);
+                pl->groups_per_slab = static_cast<int>(groups_per_slab);
+                pl->off_groupmax = carve(sizeof(uint32_t) * q_pad * groups);
+            }
+        }
         if (p->precision == RADAR_PREC_FP32) {
             // exact re-run of uncertified queries: enqueued unconditionally with a device-side count, sized for all q
             const int64_t fq = q;
@@ -538,6 +561,9 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         fl.apack = reinterpret_cast<uint16_t*>(ws + pl.off_apack);
         fl.units = pl.units; fl.device_sms = di.sms;
         fl.dbg_scores = nullptr;
+        fl.groups = pl.groups; fl.group_tiles = pl.group_tiles; fl.tile_stride = pl.tile_stride;
+        fl.groups_per_slab = pl.groups_per_slab;
+        fl.groupmax = pl.groups ? reinterpret_cast<uint32_t*>(ws + pl.off_groupmax) : nullptr;
         fl.ev_start = g_prof_start; fl.ev_stop = g_prof_stop;
         int nl = 0;
         rc = tc::launch_filter(fl, st, &nl);

@@ -262,6 +262,14 @@ struct FilterArgs {
     unsigned long long* progress;  // [units] (round << 32 | tiles loaded) of every pair; zeroed before the launch
     int window;         // tiles a pair may run ahead of the slowest pair sweeping the same slab (0 = unbounded)
     float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
+    // KL threshold prepass (see launch_filter): prepass = 1 -> the epilogue only records, per query, the maximum key of every
+    // group of `group_tiles` consecutive sampled tiles of a slab (groupmax[qrow][slab][group], ord-encoded); the k'-th largest
+    // group maximum is then a near-exact initial threshold for the real pass (gthr_init = 1), which so sees ~k' survivors
+    // per query instead of the ~k' ln(n) of a cold start
+    uint32_t* groupmax;
+    int prepass, gthr_init, group_tiles, groups, groups_per_slab;
+    int tile_stride;    // 1, or > 1 in the prepass: only every tile_stride-th tile of a slab is visited (a sample still
+                        // yields a valid, slightly looser threshold at 1/tile_stride of the cost)
     int dbg_flags;      // measurement aid (RADAR_TC_DBG, results are garbage): 1 = epilogue only recycles the
                         // accumulators, 2 = no TMA loads (MMAs run on whatever is in shared memory), 4 = epilogue
                         // loads the accumulators but does not look at them
@@ -374,6 +382,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     const int64_t unit = blockIdx.x >> 1;        // work-tile processor id (CTA pair)
     const int64_t units = gridDim.x >> 1;
     const int64_t items = a.q_tiles * a.parts;
+    const int64_t tile_step = static_cast<int64_t>(BLOCK_N) * a.tile_stride;  // the prepass samples every tile_stride-th tile
 
     unsigned long long clk0 = 0, ns0 = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -418,7 +427,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             const int peer_lo = static_cast<int>(max(static_cast<int64_t>(0), part * a.q_tiles - round_base));
             const int peer_hi = static_cast<int>(min(min(units, items - round_base), (part + 1) * a.q_tiles - round_base));
             uint32_t j = 0;
-            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N, ++j) {
+            for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step, ++j) {
                 if (publish && (j % kProgressEvery) == 0) {
                     const unsigned long long mine = (static_cast<unsigned long long>(round) << 32) | j;
                     if (lane == 0) st_progress(a.progress + unit, mine);
@@ -486,7 +495,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
                 mbar_wait(aready_bar, item_no & 1);  // this item's query tile is in TMEM (both CTAs)
                 tc_fence_after();
-                for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
+                for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
                     mbar_wait(&tempty_bar[as], aph ^ 1);  // epilogues drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = ACC_COL0 + as * BLOCK_N;  // TMEM base is 0: the pair owns all 512 columns
@@ -580,13 +589,18 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             const float shift = a.qshift[qrow];
             // start from the best threshold an earlier slab of this query published (a lower bound on the k'-th best
             // key over the whole corpus, so dropping below it is always safe)
-            const uint32_t g0 = a.parts > 1 ? *reinterpret_cast<volatile const uint32_t*>(a.gthr + qrow) : 0u;
+            const uint32_t g0 = (a.parts > 1 || a.gthr_init) ? *reinterpret_cast<volatile const uint32_t*>(a.gthr + qrow) : 0u;
             float thr = g0 ? ord2f(g0) : -CUDART_INF_F;                    // in canonical-key units
             float thr_cmp = valid ? (g0 ? __fadd_rn(thr, shift) : -CUDART_INF_F) : CUDART_INF_F;  // accumulator units
+            // an inherited threshold is the key of some case computed as fl(acc - shift); fl(thr + shift) may round ABOVE that
+            // case's accumulator, and cases tied with it (duplicates, possibly with smaller ids) would then be dropped:
+            // step a few ulps down -- a lower threshold is always safe
+            if (valid && g0) thr_cmp -= 4e-7f * (fabsf(thr_cmp) + fabsf(shift));
             int cnt = 0;
             uint64_t* buf = a.cand + (qrow * a.parts + part) * kCandCap;
+            float gmax = -CUDART_INF_F;  // prepass: running maximum of the current tile group
 
-            for (int64_t row0 = row_begin; row0 < row_end; row0 += BLOCK_N) {
+            for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
                 const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N;
@@ -612,6 +626,29 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 }
                 if (a.dbg_flags & 5) {
                     if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[BLOCK_N - 1]));
+                    continue;
+                }
+                if (a.prepass) {
+                    float m;
+                    if (row0 + BLOCK_N <= row_end) {
+                        m = v[0];
+#pragma unroll
+                        for (int jj = 1; jj < BLOCK_N; ++jj) m = fmaxf(m, v[jj]);
+                    } else {  // ragged last tile: rows past the end were zero-filled by TMA and must not count
+                        m = -CUDART_INF_F;
+#pragma unroll
+                        for (int jj = 0; jj < BLOCK_N; ++jj)
+                            if (row0 + jj < row_end) m = fmaxf(m, v[jj]);
+                    }
+                    gmax = fmaxf(gmax, m);
+                    const int64_t tile_no = (row0 - row_begin) / tile_step;  // index among this slab's sampled tiles
+                    const bool group_ends = ((tile_no + 1) % a.group_tiles) == 0 || row0 + tile_step >= row_end;
+                    if (group_ends) {
+                        if (valid)
+                            a.groupmax[qrow * a.groups + part * a.groups_per_slab + tile_no / a.group_tiles] =
+                                f2ord(__fsub_rn(gmax, shift));
+                        gmax = -CUDART_INF_F;
+                    }
                     continue;
                 }
 #pragma unroll
@@ -663,6 +700,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     }
                 }
             }
+            if (a.prepass) continue;
             a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
             a.thr[qrow * a.parts + part] = thr;
             if (a.parts > 1 && valid && thr > -CUDART_INF_F) atomicMax(a.gthr + qrow, f2ord(thr));
@@ -739,6 +777,8 @@ struct FilterLaunch {
     int units;        // CTA pairs to launch (<= kMaxUnits)
     int device_sms;   // SMs of the device (the window is only honoured when every CTA is resident)
     float* dbg_scores;
+    uint32_t* groupmax;  // [q_pad][groups] when the KL threshold prepass is planned (groups > 0), else unused
+    int groups, group_tiles, tile_stride, groups_per_slab;
     cudaEvent_t ev_start, ev_stop;  // optional: recorded around the filter kernel only
     unsigned long long* clk_dev;    // out: device address of the {cycles, ns} pair the kernel writes
 };
@@ -796,6 +836,34 @@ static inline void fill_col_max(const radar_corpus_t* c, float* out) {
     for (int j = 0; j < kObsPad; ++j) out[j] = given ? c->logq_col_max[j] * 1.0001f : c->logq_max_abs;
 }
 
+// k'-th largest group maximum per query (one warp per query) -> initial threshold of the real pass
+constexpr int kMaxGroups32 = 16;  // up to 512 groups per query
+__global__ void __launch_bounds__(256) group_threshold_kernel(const uint32_t* __restrict__ groupmax, int64_t q, int groups,
+                                                              int kp, uint32_t* __restrict__ gthr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qi = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (qi >= q) return;
+    const uint32_t* src = groupmax + qi * groups;
+    uint32_t val[kMaxGroups32];
+#pragma unroll
+    for (int e = 0; e < kMaxGroups32; ++e) {
+        const int i = lane + 32 * e;
+        val[e] = i < groups ? src[i] : 0u;
+    }
+    uint32_t key = 0;
+    if (groups >= kp) {
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = key | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < kMaxGroups32; ++e) c += val[e] >= trial ? 1 : 0;
+            if (__reduce_add_sync(0xffffffffu, c) >= kp) key = trial;
+        }
+    }
+    if (lane == 0) gthr[qi] = key;  // 0 = no threshold
+}
+
 // apack region layout: [q_pad * a_cols] uint16, then (256-byte aligned) qshift [q_pad] floats
 static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
     size_t b = sizeof(uint16_t) * static_cast<size_t>(q_pad) * a_cols_for(mode, d);
@@ -822,6 +890,7 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
     fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.gthr = fl.gthr; fa.dbg_scores = fl.dbg_scores;
     fa.dbg_flags = getenv("RADAR_TC_DBG") ? atoi(getenv("RADAR_TC_DBG")) : 0;
+    fa.tile_stride = 1;
     fa.progress = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(fl.gthr) +
                                                         (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8);
     fa.clk = fa.progress + kMaxUnits;
@@ -836,6 +905,26 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     fa.window = (resident && fl.q_tiles > 1 && getenv("RADAR_TC_NO_WINDOW") == nullptr) ? static_cast<int>(window) : 0;
     int rc;
     const bool d512 = fl.corpus->d == 512;
+    *launches = 2;
+    if (fl.mode == RADAR_MODE_KL && fl.groups > 0 && fl.dbg_scores == nullptr) {
+        // two-pass KL: (1) group maxima, (2) k'-th largest -> gthr, (3) the real pass starts from near-exact thresholds
+        RADAR_CUDA_CHECK(cudaMemsetAsync(fl.groupmax, 0, sizeof(uint32_t) * static_cast<size_t>(q_pad) * fl.groups, st));
+        FilterArgs fp = fa;
+        fp.prepass = 1; fp.groupmax = fl.groupmax; fp.groups = fl.groups; fp.group_tiles = fl.group_tiles;
+        fp.tile_stride = fl.tile_stride; fp.groups_per_slab = fl.groups_per_slab;
+        cudaEvent_t e0 = fl.ev_start, e1 = fl.ev_stop;
+        fl.ev_start = fl.ev_stop = nullptr;  // the profiled kernel is the real pass
+        rc = launch_filter_mode<RADAR_MODE_KL, 0>(fl, fp, st);
+        fl.ev_start = e0; fl.ev_stop = e1;
+        if (rc) return rc;
+        group_threshold_kernel<<<static_cast<unsigned>((fl.q * 32 + 255) / 256), 256, 0, st>>>(fl.groupmax, fl.q, fl.groups,
+                                                                                                 fl.kp, fl.gthr);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        // the progress words of the window protocol must start from zero again
+        RADAR_CUDA_CHECK(cudaMemsetAsync(fa.progress, 0, sizeof(unsigned long long) * kMaxUnits, st));
+        fa.gthr_init = 1;
+        *launches += 2;
+    }
     if (fl.mode == RADAR_MODE_KL) rc = launch_filter_mode<RADAR_MODE_KL, 0>(fl, fa, st);
     else if (fl.mode == RADAR_MODE_DPR)
         rc = d512 ? launch_filter_mode<RADAR_MODE_DPR, 8>(fl, fa, st) : launch_filter_mode<RADAR_MODE_DPR, 0>(fl, fa, st);
@@ -843,7 +932,6 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
         rc = d512 ? launch_filter_mode<RADAR_MODE_HYBRID, 8>(fl, fa, st)
                   : launch_filter_mode<RADAR_MODE_HYBRID, 0>(fl, fa, st);
     if (rc) return rc;
-    *launches = 2;
     return RADAR_OK;
 }
 
