@@ -620,3 +620,29 @@ def test_index_save_load_round_trip(dev, tmp_path):
     ws, wi = _oracle(p, "hybrid", 10, idx_offset=1000)
     s1, i1 = _search(back, p, "hybrid", 10)
     assert np.array_equal(i1, wi) and np.array_equal(s1, ws)
+
+
+@pytest.mark.parametrize("mode,n,q", [("hybrid", 20000, 300), ("kl", 70000, 16)])
+def test_graphed_search_replay_equals_eager(dev, mode, n, q):
+    """A search chain captured in a CUDA graph (GraphedSearch) returns what the eager call returns, also after the
+    static input tensors have been overwritten with new queries."""
+    from radar_multimodal_radiology_b200.index import GraphedSearch
+    p = make_problem(n, q, d=64 if mode == "kl" else 512, seed=51)
+    idx = _index(p, dev, precision="fp32")
+    xq = None if mode == "kl" else torch.from_numpy(p["q_emb"]).to(dev)
+    pr = torch.from_numpy(p["q_pr"]).to(dev)
+    mk = torch.from_numpy(p["mask"]).to(dev)
+    g = GraphedSearch(idx, xq, 10, query_probs=pr, mask=mk, alpha=0.5, mode=mode)
+    s, i = g.replay()
+    torch.cuda.synchronize()
+    ws, wi = _oracle(p, mode, 10)
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+    p2 = make_problem(n, q, d=64 if mode == "kl" else 512, seed=52)  # same corpus seed offset differs -> new queries only
+    pr.copy_(torch.from_numpy(p2["q_pr"]))
+    if xq is not None:
+        xq.copy_(torch.from_numpy(p2["q_emb"]))
+    s, i = g.replay()
+    torch.cuda.synchronize()
+    p_new = dict(p, q_pr=p2["q_pr"], q_emb=p2["q_emb"])
+    ws, wi = _oracle(p_new, mode, 10)
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
