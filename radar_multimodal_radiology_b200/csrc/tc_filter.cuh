@@ -631,9 +631,12 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 if (a.prepass) {
                     float m;
                     if (row0 + BLOCK_N <= row_end) {
-                        m = v[0];
+                        float mm[8];  // eight independent chains: the epilogue warp is alone on its scheduler, ILP is all it has
 #pragma unroll
-                        for (int jj = 1; jj < BLOCK_N; ++jj) m = fmaxf(m, v[jj]);
+                        for (int u = 0; u < 8; ++u) mm[u] = v[u];
+#pragma unroll
+                        for (int jj = 8; jj < BLOCK_N; ++jj) mm[jj & 7] = fmaxf(mm[jj & 7], v[jj]);
+                        m = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), fmaxf(fmaxf(mm[4], mm[5]), fmaxf(mm[6], mm[7])));
                     } else {  // ragged last tile: rows past the end were zero-filled by TMA and must not count
                         m = -CUDART_INF_F;
 #pragma unroll
@@ -654,10 +657,11 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
 #pragma unroll
                 for (int c = 0; c < BLOCK_N; c += 32) {
                     const int width = (BLOCK_N - c) < 32 ? (BLOCK_N - c) : 32;  // 32 or 16 (compile time after unroll)
-                    float m = v[c];
+                    float mm[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};  // four independent chains (ILP)
 #pragma unroll
-                    for (int jj = 1; jj < 32; ++jj)
-                        if (jj < width) m = fmaxf(m, v[c + jj]);
+                    for (int jj = 4; jj < 32; ++jj)
+                        if (jj < width) mm[jj & 3] = fmaxf(mm[jj & 3], v[c + jj]);
+                    const float m = fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
                     if (__any_sync(0xffffffffu, m >= thr_cmp) || a.dbg_scores) {
                         // rare path, written for a small instruction footprint (it used to be unrolled per column and
                         // pushed the kernel far beyond the instruction cache): the chunk is staged in this warp's
