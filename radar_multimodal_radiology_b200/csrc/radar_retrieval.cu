@@ -60,6 +60,7 @@ struct Plan {
     int tile_q;        // rows per query tile (64 scan / 256 filter)
     int units;         // CTA pairs the filter launches
     int parts;
+    int buf_parts;     // candidate buffers per query row: slabs x epilogue warp sets
     int64_t rows_per_part;
     // workspace offsets (bytes)
     size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
@@ -219,9 +220,10 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         plan_parts_filter(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), units, &pl->parts, &pl->rows_per_part);
     }
     const int64_t q_pad = pl->q_tiles * pl->tile_q;
-    pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->parts * kCandCap);
-    pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->parts);
-    pl->off_thr = carve(sizeof(float) * q_pad * pl->parts);
+    pl->buf_parts = pl->parts * (algo == RADAR_ALGO_TC_FILTER ? tc::epi_sets_for_mode(p->mode) : 1);
+    pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->buf_parts * kCandCap);
+    pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->buf_parts);
+    pl->off_thr = carve(sizeof(float) * q_pad * pl->buf_parts);
     pl->off_gthr = carve(tc::gthr_region_bytes(q_pad));
     pl->off_sel = carve(sizeof(uint64_t) * q * pl->R);
     pl->off_bound = carve(sizeof(float) * q);
@@ -571,7 +573,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         clk_dev = fl.clk_dev;
         launches += nl;
         select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
-            cand, cnt, thr, q, nullptr, pl.parts, kCandCap, pl.R, sel, bound);
+            cand, cnt, thr, q, nullptr, pl.buf_parts, kCandCap, pl.R, sel, bound);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         RescoreArgs r{};

@@ -38,7 +38,7 @@ namespace tc {
 
 constexpr int kBlockM = 128;          // query rows per CTA == TMEM lanes
 constexpr int kTileQ = 2 * kBlockM;   // query rows per work tile (CTA pair)
-constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue (+ warps 6..9 in KL mode)
 constexpr int kTmemCols = 512;
 constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
 constexpr int kRingBytes = 192 * 1024;  // shared-memory ring of tile slots (per CTA)
@@ -51,6 +51,10 @@ constexpr uint32_t kWindowSpinLimit = 1u << 16;  // polls (x ~1 us) before a pai
 
 __host__ __device__ constexpr int block_n_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? 112 : 128; }
 __host__ __device__ constexpr int acc_stages_for_mode(int mode) { return mode == RADAR_MODE_KL ? 3 : 2; }
+// Epilogue warp sets.  A KL tile is three K = 16 MMAs, so in KL mode the threshold filter -- not the tensor pipe -- is the
+// bound: two sets of four warps split every tile's columns (each set keeps its own candidate buffers and thresholds).
+__host__ __device__ constexpr int epi_sets_for_mode(int mode) { return mode == RADAR_MODE_KL ? 2 : 1; }
+__host__ __device__ constexpr int threads_for_mode(int mode) { return 64 + 128 * epi_sets_for_mode(mode); }
 __host__ __device__ constexpr int acc_col0_for_mode(int mode) {
     return mode == RADAR_MODE_DPR ? kAIpCols : (mode == RADAR_MODE_HYBRID ? kAIpCols + 32 : 128);
 }
@@ -71,7 +75,7 @@ __host__ __device__ constexpr int slots_for(int mode, int kblocks) {
 }
 __host__ __device__ constexpr int groups_for(int kblocks) { return kblocks <= 1 ? 1 : (kblocks + 1) / 2; }
 
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 4 * 32 * 32 * sizeof(float) /*chunk staging*/ +
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 8 * 32 * 32 * sizeof(float) /*chunk staging*/ +
                               1024 /*barriers*/;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -254,9 +258,9 @@ struct FilterArgs {
     int parts;
     int64_t rows_per_part;  // multiple of BLOCK_N
     int kp;
-    uint64_t* cand;     // [q_pad][parts][kCandCap]
-    uint32_t* cnt;      // [q_pad][parts]
-    float* thr;         // [q_pad][parts]  final thresholds
+    uint64_t* cand;     // [q_pad][parts][epilogue sets][kCandCap]
+    uint32_t* cnt;      // [q_pad][parts][epilogue sets]
+    float* thr;         // [q_pad][parts][epilogue sets]  final thresholds
     uint32_t* gthr;     // [q_pad] best published threshold per query (ord-encoded, 0 = none): slabs of the same
                         // query tile that run later start from it instead of -inf
     unsigned long long* progress;  // [units] (round << 32 | tiles loaded) of every pair; zeroed before the launch
@@ -343,7 +347,7 @@ __device__ __forceinline__ void st_progress(unsigned long long* p, unsigned long
 // KB_T > 0: the embedding K-block count (d / 64) is a compile-time constant and the issue / load loops unroll
 // completely (KB_T = 8 is BiomedCLIP's d = 512); KB_T = 0: d is read from the arguments.
 template <int MODE, int KB_T>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(threads_for_mode(MODE), 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_constant__ CUtensorMap map_kl,
                  const FilterArgs a) {
     constexpr bool HAS_IP = MODE != RADAR_MODE_KL;
@@ -351,6 +355,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     constexpr int BLOCK_N = block_n_for_mode(MODE);     // corpus rows per MMA tile (whole pair)
     constexpr int LOAD_N = BLOCK_N / 2;                 // corpus rows this CTA stages per tile
     constexpr int ACC_STAGES = acc_stages_for_mode(MODE);
+    constexpr int EPI_SETS = epi_sets_for_mode(MODE);
+    constexpr int COLS = BLOCK_N / EPI_SETS;            // accumulator columns one epilogue warp looks at
     constexpr int ACC_COL0 = acc_col0_for_mode(MODE);
     constexpr int A_KL_COL = a_kl_col_for_mode(MODE);
     constexpr uint32_t IDESC = make_idesc_mn(kTileQ, BLOCK_N);
@@ -367,7 +373,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float* stage = reinterpret_cast<float*>(smem + kRingBytes);               // [4 warps][32 columns][32 lanes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * 32 * 32);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 8 * 32 * 32);
     uint64_t* full_bar = bars;                                   // [kMaxSlots][kMaxGroups] (only the leader's are waited on)
     uint64_t* empty_bar = full_bar + kMaxSlots * kMaxGroups;      // [kMaxSlots]
     uint64_t* tfull_bar = empty_bar + kMaxSlots;                  // [ACC_STAGES]
@@ -396,7 +402,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
         for (int i = 0; i < kMaxSlots; ++i) mbar_init(&empty_bar[i], 1);
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8);
+            mbar_init(&tempty_bar[i], 8 * EPI_SETS);
         }
         mbar_init(aready_bar, 8);
         fence_barrier_init();
@@ -549,8 +555,10 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             }
         }
     } else {
-        // ================================ epilogue warps (2..5) ================================
+        // ================================ epilogue warps (2..5, and 6..9 with two sets) ================================
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int set = (warp - 2) >> 2;   // which COLS-wide column range of every tile this warp filters
+        const int col0 = set * COLS;
         const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
         const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
         float* my_stage = stage + (warp - 2) * 32 * 32 + lane;  // [column * 32]: bank == lane, no conflicts
@@ -564,7 +572,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
             const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
             // ---- A tile -> TMEM (every MMA of the previous item has completed: its last accumulator was consumed) ----
-            {
+            if (set == 0) {
                 const uint4* src = reinterpret_cast<const uint4*>(a.apack + qrow * a_cols);
                 const int ip_chunks = HAS_IP ? a.d / 16 : 0;  // 16 bf16 = 8 TMEM columns per chunk
                 for (int c = 0; c < ip_chunks; ++c) {
@@ -597,22 +605,24 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
             // step a few ulps down -- a lower threshold is always safe
             if (valid && g0) thr_cmp -= 4e-7f * (fabsf(thr_cmp) + fabsf(shift));
             int cnt = 0;
-            uint64_t* buf = a.cand + (qrow * a.parts + part) * kCandCap;
+            const int64_t slot_idx = (qrow * a.parts + part) * EPI_SETS + set;  // this warp set's private buffer
+            uint64_t* buf = a.cand + slot_idx * kCandCap;
             float gmax = -CUDART_INF_F;  // prepass: running maximum of the current tile group
 
             for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
-                const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N;
+                const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + as * BLOCK_N + col0;
+                const int64_t rowc = row0 + col0;  // corpus row of this warp's first column
                 // The whole accumulator row goes to registers with back-to-back tcgen05.ld, then the TMEM stage is
                 // handed back to the MMA issuer BEFORE the values are looked at: the threshold filter below (and its
                 // occasional candidate insertions / compactions) overlaps the next tile's MMAs instead of sitting
                 // between two of them.
-                float v[BLOCK_N];
+                float v[COLS];
                 if (!(a.dbg_flags & 1)) {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N; c += 32) {
-                        if (BLOCK_N - c >= 32) tmem_ld_x32(t_acc + c, v + c);
+                    for (int c = 0; c < COLS; c += 32) {
+                        if (COLS - c >= 32) tmem_ld_x32(t_acc + c, v + c);
                         else tmem_ld_x16(t_acc + c, v + c);
                     }
                     tmem_wait_ld();
@@ -625,7 +635,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     aph ^= 1;
                 }
                 if (a.dbg_flags & 5) {
-                    if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[BLOCK_N - 1]));
+                    if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[COLS - 1]));
                     continue;
                 }
                 if (a.prepass) {
@@ -635,28 +645,28 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
 #pragma unroll
                         for (int u = 0; u < 8; ++u) mm[u] = v[u];
 #pragma unroll
-                        for (int jj = 8; jj < BLOCK_N; ++jj) mm[jj & 7] = fmaxf(mm[jj & 7], v[jj]);
+                        for (int jj = 8; jj < COLS; ++jj) mm[jj & 7] = fmaxf(mm[jj & 7], v[jj]);
                         m = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), fmaxf(fmaxf(mm[4], mm[5]), fmaxf(mm[6], mm[7])));
                     } else {  // ragged last tile: rows past the end were zero-filled by TMA and must not count
                         m = -CUDART_INF_F;
 #pragma unroll
-                        for (int jj = 0; jj < BLOCK_N; ++jj)
-                            if (row0 + jj < row_end) m = fmaxf(m, v[jj]);
+                        for (int jj = 0; jj < COLS; ++jj)
+                            if (rowc + jj < row_end) m = fmaxf(m, v[jj]);
                     }
                     gmax = fmaxf(gmax, m);
                     const int64_t tile_no = (row0 - row_begin) / tile_step;  // index among this slab's sampled tiles
                     const bool group_ends = ((tile_no + 1) % a.group_tiles) == 0 || row0 + tile_step >= row_end;
                     if (group_ends) {
-                        if (valid)
-                            a.groupmax[qrow * a.groups + part * a.groups_per_slab + tile_no / a.group_tiles] =
-                                f2ord(__fsub_rn(gmax, shift));
+                        if (valid)  // both warp sets feed the same group slot
+                            atomicMax(a.groupmax + qrow * a.groups + part * a.groups_per_slab + tile_no / a.group_tiles,
+                                      f2ord(__fsub_rn(gmax, shift)));
                         gmax = -CUDART_INF_F;
                     }
                     continue;
                 }
 #pragma unroll
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    const int width = (BLOCK_N - c) < 32 ? (BLOCK_N - c) : 32;  // 32 or 16 (compile time after unroll)
+                for (int c = 0; c < COLS; c += 32) {
+                    const int width = (COLS - c) < 32 ? (COLS - c) : 32;  // 32 or 16 (compile time after unroll)
                     float mm[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]};  // four independent chains (ILP)
 #pragma unroll
                     for (int jj = 4; jj < 32; ++jj)
@@ -676,9 +686,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                         }
                         if (a.dbg_scores && valid) {
                             for (int jj = 0; jj < width; ++jj)
-                                if (row0 + c + jj < a.n) a.dbg_scores[qrow * a.n + row0 + c + jj] = my_stage[jj * 32] - shift;
+                                if (rowc + c + jj < a.n) a.dbg_scores[qrow * a.n + rowc + c + jj] = my_stage[jj * 32] - shift;
                         }
-                        const int64_t row_base = row0 + c;
+                        const int64_t row_base = rowc + c;
                         while (mask) {
                             const int jj = __ffs(mask) - 1;
                             mask &= mask - 1;
@@ -705,8 +715,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 }
             }
             if (a.prepass) continue;
-            a.cnt[qrow * a.parts + part] = valid ? static_cast<uint32_t>(cnt) : 0u;
-            a.thr[qrow * a.parts + part] = thr;
+            a.cnt[slot_idx] = valid ? static_cast<uint32_t>(cnt) : 0u;
+            a.thr[slot_idx] = thr;
             if (a.parts > 1 && valid && thr > -CUDART_INF_F) atomicMax(a.gthr + qrow, f2ord(thr));
         }
     }
@@ -817,7 +827,7 @@ static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cuda
     if (units > items) units = items;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads_for_mode(MODE));
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
