@@ -51,7 +51,7 @@ __host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one quer
     int c = (1 << 20) / n_pad;
     return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
 }
-__host__ __device__ inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
+inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
     int64_t s = 32768 / n_pad;
     if (s < 256) s = 256;
     if (s > kMaxSample) s = kMaxSample;
@@ -170,6 +170,7 @@ struct StreamArgs {
     uint32_t* best_n;            // [n_pad]
     uint64_t* best;              // [n_pad][kCandCap] running best-k' list of every query (touched under the lock only)
     uint64_t* pool;              // [n_pad][pool_cap]
+    int reload;                  // super-tiles (of one epilogue set) between reloads of the published thresholds
 };
 
 constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
@@ -441,7 +442,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             const int64_t t = unit + static_cast<int64_t>(j) * units;
             if (t >= a.tiles) break;
             const uint32_t sp = j & sp_mask, aph = (j >> sp_shift) & 1u;
-            if (++since == kThrReload) {  // use the values requested a few super-tiles ago, request fresh ones
+            if (++since == static_cast<uint32_t>(a.reload)) {  // use the values requested a few super-tiles ago, request fresh ones
                 since = 0;
                 commit_thresholds();
 #pragma unroll

@@ -496,6 +496,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         sa.n = corpus->n; sa.tiles = pl.tiles; sa.q = static_cast<int>(q); sa.n_pad = pl.n_pad; sa.kp = pl.kp;
         sa.pool_cap = pl.pool_cap; sa.qshift = qshift; sa.gthr = gthr; sa.gcnt = gcnt; sa.lock = lock;
         sa.processed = processed; sa.best_n = best_n; sa.best = best; sa.pool = pool;
+        sa.reload = kls::kThrReload;  // measured: 4 beats 1, 2, 8, 16 on kl_latency (fresher thresholds vs reload cost)
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(kls::kl_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kls::kStreamSmemBytes)));
         int64_t units = pl.units;
