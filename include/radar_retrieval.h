@@ -163,7 +163,11 @@ size_t radar_search_workspace_bytes(const radar_corpus_t* corpus, int64_t q,
 
 /* out_scores [q,k] float32 in the API's sign (DPR: ip desc; KL: KL asc; hybrid: fused desc),
  * out_idx [q,k] int64 (+ corpus->idx_offset).  workspace: device memory of at least
- * radar_search_workspace_bytes(...).  stats: optional HOST pointer. */
+ * radar_search_workspace_bytes(...).  stats: optional HOST pointer (NULL: the call only enqueues work and never
+ * synchronises -- it can be captured in a CUDA graph; queries whose FP32 certificate fails, or whose pooled buffer
+ * overflowed on the KL stream path, are re-run by the exact scan with a device-side count, without a host round trip).
+ * RADAR_ALGO_AUTO picks RADAR_ALGO_KL_STREAM for KL with <= 256 queries over >= 65 536 cases, otherwise the tcgen05
+ * filter when the corpus carries the bf16 tables, otherwise the exact scan. */
 int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries,
                  const radar_search_params_t* params, float* out_scores, int64_t* out_idx,
                  void* workspace, size_t workspace_bytes, radar_search_stats_t* stats, void* stream);
