@@ -404,7 +404,10 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 if (i < nq32) {
                     const int qi = lane + 32 * i;
                     const float tk = pending[i] ? ord2f(pending[i]) : -CUDART_INF_F;
-                    my_thr[qi] = qi < a.q ? (pending[i] ? __fadd_rn(tk, h_s[qi]) : -CUDART_INF_F) : CUDART_INF_F;
+                    // a few ulps below fl(key + H): fl(fl(acc - H) + H) may round above acc, and cases tied with the
+                    // threshold must not be lost (a lower threshold is always safe)
+                    const float ta = __fadd_rn(tk, h_s[qi]);
+                    my_thr[qi] = qi < a.q ? (pending[i] ? ta - 4e-7f * (fabsf(ta) + fabsf(h_s[qi])) : -CUDART_INF_F) : CUDART_INF_F;
                 }
             }
             __syncwarp();
