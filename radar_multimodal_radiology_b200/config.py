@@ -9,7 +9,7 @@ B200 path adds ("Config / flags").
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass, field, fields
+from dataclasses import dataclass, fields
 from typing import List, Optional
 
 _REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

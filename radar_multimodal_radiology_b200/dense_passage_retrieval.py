@@ -28,7 +28,7 @@ import torch.nn as nn
 
 from .config import RetrievalConfig
 from .index import RadarIndex, project_normalize
-from .knowledge import OBSERVATION_NAMES, observation_bits
+from .knowledge import OBSERVATION_NAMES, observation_bits  # noqa: F401 (re-exported)
 
 logger = logging.getLogger(__name__)
 

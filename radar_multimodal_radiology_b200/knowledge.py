@@ -13,7 +13,7 @@ The arithmetic runs in the sm_100a kernels behind ``RadarIndex``; nothing here c
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, List, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -8,7 +8,6 @@ normals plus a 20 GB upload would dominate the run) and the CPU baseline reads a
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
 
 import torch
 
