@@ -264,7 +264,7 @@ def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
 # ---------------------------------------------------------------------------------------------------
 # KL stream path (few queries, large corpus: pooled candidates, tcgen05 with cases on the M side)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("q", [1, 7, 32, 33, 200])
+@pytest.mark.parametrize("q", [1, 7, 32, 33, 100, 200])
 @pytest.mark.parametrize("k", [1, 10, 32, 128])
 def test_kl_stream_fp32_is_bit_identical(dev, q, k):
     p = make_problem(70001, q, d=64, seed=20 + q)
