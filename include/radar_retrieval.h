@@ -37,12 +37,12 @@
 extern "C" {
 #endif
 
-#define RADAR_ABI_VERSION 2
+#define RADAR_ABI_VERSION 3
 
 #define RADAR_NUM_OBS 14 /* CheXpert-14, train_expert_models.py:50-65 */
 #define RADAR_OBS_PAD 16 /* K=16 padded contraction */
 #define RADAR_KLPACK 32  /* bf16 [log q hi (16) | log q lo (16)] per corpus row = 64 B */
-#define RADAR_MAX_K 128  /* largest top-k per call */
+#define RADAR_MAX_K 128  /* largest top-k per radar_search call; larger k: page with radar_queries.after_* */
 
 enum radar_status {
     RADAR_OK = 0,
@@ -96,6 +96,14 @@ typedef struct radar_queries {
     const float* emb_f32; /* [q,d]   */
     const float* p16;     /* [q,16]  masked, clamped probabilities (radar_kl_prepare_queries) */
     const float* entropy; /* [q]     sum_j p16_j log p16_j (radar_kl_prepare_queries) */
+    /* "search after" (both NULL: off).  When given, query i only returns cases that rank STRICTLY AFTER the pair
+     * (after_scores[i], after_idx[i]) -- a score/id pair as a previous radar_search returned it (API sign, global
+     * id) -- under the (score, id) order; after_idx[i] < 0 switches the bound off for that query.  This pages
+     * through a ranking: IndexFlatIP.search accepts any k (dpr.py:313, retrieve_with_hard_negatives dpr.py:326
+     * asks for k + num_negatives), so k > RADAR_MAX_K is served as ceil(k / RADAR_MAX_K) calls.  Exact scan only
+     * (RADAR_ALGO_AUTO selects it; other algorithms return RADAR_E_ARG). */
+    const float* after_scores; /* [q] */
+    const int64_t* after_idx;  /* [q] */
 } radar_queries_t;
 
 typedef struct radar_search_params {
@@ -129,6 +137,9 @@ int radar_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* make `device` current for this thread inside the library's CUDA runtime (call before any other entry
  * point when the process drives more than one GPU; one process per GPU under torchrun needs it once). */
 int radar_set_device(int device);
+/* the device that is current for this thread in the library's CUDA runtime (host output); callers that switch
+ * devices around a call use it to restore the previous one */
+int radar_get_device(int* device);
 
 /* measurement aid: while enabled, every radar_search call of this thread records a pair of CUDA events
  * (owned by the library) immediately before / after its dominant kernel (exact scan or tensor-core
@@ -166,18 +177,25 @@ size_t radar_search_workspace_bytes(const radar_corpus_t* corpus, int64_t q,
  * radar_search_workspace_bytes(...).  stats: optional HOST pointer (NULL: the call only enqueues work and never
  * synchronises -- it can be captured in a CUDA graph; queries whose FP32 certificate fails, or whose pooled buffer
  * overflowed on the KL stream path, are re-run by the exact scan with a device-side count, without a host round trip).
+ * out_packed (nullable) [q,k] uint64: the same result as one sortable word per entry,
+ *   (orderable bits of the ranking key << 32) | (0xFFFFFFFF - global id), 0 = padding; larger word = better rank.
+ *   It is what row-sharded ranks exchange (ONE all-gather of 8 B per entry) before radar_merge_packed.
  * RADAR_ALGO_AUTO picks RADAR_ALGO_KL_STREAM for KL with <= 256 queries over >= 65 536 cases, otherwise the tcgen05
  * filter when the corpus carries the bf16 tables, otherwise the exact scan. */
 int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries,
                  const radar_search_params_t* params, float* out_scores, int64_t* out_idx,
-                 void* workspace, size_t workspace_bytes, radar_search_stats_t* stats, void* stream);
+                 uint64_t* out_packed, void* workspace, size_t workspace_bytes, radar_search_stats_t* stats,
+                 void* stream);
 
-/* bring-up / test aid: dense dump of the tensor-core filter keys (canonical-key units) for every
- * (query, case) pair into out_keys [q,n] -- only sensible for small q*n.  Same workspace as radar_search
- * with algo = RADAR_ALGO_TC_FILTER. */
+#ifdef RADAR_DEBUG
+/* bring-up / test aid, exported ONLY by the RADAR_DEBUG flavour of the library (libradar_retrieval_dbg.so; the
+ * release library neither declares nor exports it and reads no environment variables): dense dump of the
+ * tensor-core filter keys (canonical-key units) for every (query, case) pair into out_keys [q,n] -- only sensible
+ * for small q*n.  Same workspace as radar_search with algo = RADAR_ALGO_TC_FILTER. */
 int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t* queries,
                             const radar_search_params_t* params, float* out_keys, void* workspace,
                             size_t workspace_bytes, void* stream);
+#endif
 
 /* ---- shard merge (no reference counterpart) --------------------------------- */
 
@@ -185,6 +203,11 @@ int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t*
  * Writes the best k_out (<= min(parts*k_in, 1024)) per query under (score, id) order. */
 int radar_merge_topk(const float* cand_scores, const int64_t* cand_idx, int64_t q, int parts, int k_in,
                      int k_out, int ascending, float* out_scores, int64_t* out_idx, void* stream);
+
+/* cand: [parts, q, k_in] packed words as radar_search's out_packed writes them (0 = padding).  Writes the best
+ * k_out (<= parts*k_in <= 2048) per query in API form: scores in the mode's sign (mode = enum radar_mode), ids. */
+int radar_merge_packed(const uint64_t* cand, int64_t q, int parts, int k_in, int k_out, int mode,
+                       float* out_scores, int64_t* out_idx, void* stream);
 
 /* ---- iterative-RAG re-rank (replaces TargetedRetriever.rank_retrieved_passages, rag.py:127-152) - */
 

@@ -111,3 +111,42 @@ def merge_topk(scores: np.ndarray, idx: np.ndarray, k_out: int, ascending: bool
     if rc != 0:
         raise RuntimeError(f"radar_oracle_merge_topk failed rc={rc}")
     return out_s, out_i
+
+
+# ---- packed exchange words (include/radar_retrieval.h: radar_search out_packed / radar_merge_packed) --------------
+# numpy restatement used by the CPU tests of the sharded host logic and as the checker of the CUDA merge kernel:
+#   word = (orderable bits of the ranking key << 32) | (0xFFFFFFFF - global id);  key = score (DPR, hybrid) or
+#   0 - score (KL, where smaller is better);  0 = padding;  larger word = better rank, smaller id wins ties.
+def _f2ord(key: np.ndarray) -> np.ndarray:
+    u = (np.asarray(key, dtype=np.float32) + np.float32(0.0)).view(np.uint32)  # -0 -> +0
+    return np.where(u & np.uint32(0x80000000), ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+
+
+def _ord2f(o: np.ndarray) -> np.ndarray:
+    o = np.asarray(o, dtype=np.uint32)
+    u = np.where(o & np.uint32(0x80000000), o & np.uint32(0x7FFFFFFF), ~o).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def pack_results(mode: int, scores: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """(scores float32[Q,k], global ids int64[Q,k], id < 0 = padding) -> int64[Q,k] holding the uint64 words."""
+    s = _f32(scores)
+    key = (np.float32(0.0) - s).astype(np.float32) if mode == MODE_KL else s
+    i = np.asarray(idx, dtype=np.int64)
+    word = (_f2ord(key).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.where(i < 0, 0, i).astype(np.uint64))
+    return np.where(i < 0, np.uint64(0), word).view(np.int64)
+
+
+def merge_packed(packed: np.ndarray, k_out: int, mode: int) -> Tuple[np.ndarray, np.ndarray]:
+    """packed: int64[parts, Q, k_in] words -> (scores float32[Q,k_out], ids int64[Q,k_out]) best first."""
+    w = np.ascontiguousarray(packed).view(np.uint64)
+    parts, nq, k_in = w.shape
+    allw = np.transpose(w, (1, 0, 2)).reshape(nq, parts * k_in)
+    top = np.sort(allw, axis=1)[:, ::-1][:, :k_out]
+    key = _ord2f((top >> np.uint64(32)).astype(np.uint32))
+    ids = (np.uint64(0xFFFFFFFF) - (top & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    scores = (np.float32(0.0) - key).astype(np.float32) if mode == MODE_KL else key.astype(np.float32)
+    empty = top == 0
+    scores = np.where(empty, np.float32(np.inf) if mode == MODE_KL else np.float32(-np.inf), scores).astype(np.float32)
+    ids = np.where(empty, -1, ids)
+    return scores, ids

@@ -73,6 +73,12 @@ __device__ __forceinline__ uint32_t composite_row(uint64_t c) {
     return 0xFFFFFFFFu - static_cast<uint32_t>(c & 0xFFFFFFFFull);
 }
 
+// composite with a shard-local row -> the exchange form with the GLOBAL id (radar_search's out_packed)
+__device__ __forceinline__ uint64_t packed_global(uint64_t c, int64_t idx_offset) {
+    const uint32_t gid = static_cast<uint32_t>(static_cast<int64_t>(composite_row(c)) + idx_offset);
+    return (c & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(0xFFFFFFFFu - gid);
+}
+
 // ---- bitonic sort, DESCENDING, of a power-of-two array in shared memory --------------------------
 // `nthreads` threads (ids tid in [0,nthreads)) cooperate; `sync()` must synchronise exactly them.
 template <typename SyncFn>

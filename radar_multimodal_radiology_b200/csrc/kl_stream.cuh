@@ -510,6 +510,7 @@ struct StreamFinalArgs {
     int64_t idx_offset;
     float* out_scores;
     int64_t* out_idx;
+    uint64_t* out_packed;  // nullable
     uint32_t* uncert_count;
     uint32_t* uncert_list;
 };
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__(kFinThreads) kl_stream_final_kernel(const Stre
         const uint64_t c = j < ns ? surv[j] : 0ull;
         a.out_scores[static_cast<int64_t>(qi) * a.k + j] = c ? api_score_from_key(RADAR_MODE_KL, composite_key(c)) : CUDART_INF_F;
         a.out_idx[static_cast<int64_t>(qi) * a.k + j] = c ? static_cast<int64_t>(composite_row(c)) + a.idx_offset : -1;
+        if (a.out_packed) a.out_packed[static_cast<int64_t>(qi) * a.k + j] = c ? packed_global(c, a.idx_offset) : 0ull;
     }
     if (tid == 0) {
         // an overflowed pool may have lost candidates; too many survivors cannot be sorted here

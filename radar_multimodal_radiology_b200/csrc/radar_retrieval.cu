@@ -17,6 +17,7 @@ namespace radar {
 static thread_local char g_err[512] = "";
 // optional CUDA events recorded around the main scan / filter kernel of the next radar_search calls
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static thread_local int g_prof_dev = -1;  // device the event pair was created on (events belong to one device)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -143,10 +144,17 @@ static bool kl_stream_supported(const radar_corpus_t* c, int64_t q, int mode, co
 }
 
 static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p, const DeviceInfo& di,
-                     Plan* pl) {
+                     Plan* pl, bool search_after = false) {
     memset(pl, 0, sizeof *pl);
     const int sms = p->num_sms > 0 ? p->num_sms : di.sms;
     int algo = p->algo;
+    if (search_after) {  // paging through a ranking is served by the exact scan only
+        if (algo != RADAR_ALGO_AUTO && algo != RADAR_ALGO_SIMT_EXACT) {
+            set_error("queries.after_scores/after_idx need RADAR_ALGO_AUTO or RADAR_ALGO_SIMT_EXACT");
+            return RADAR_E_ARG;
+        }
+        algo = RADAR_ALGO_SIMT_EXACT;
+    }
     if (algo == RADAR_ALGO_AUTO) {
         if (kl_stream_supported(c, q, p->mode, di) && p->num_sms == 0) algo = RADAR_ALGO_KL_STREAM;
         else algo = tc_supported(c, p->mode, di) ? RADAR_ALGO_TC_FILTER : RADAR_ALGO_SIMT_EXACT;
@@ -302,7 +310,7 @@ static int launch_scan(const ScanArgs& a, int64_t q_tiles, cudaStream_t st) {
 static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_t* queries, int mode, int k, float alpha,
                               float oma, int64_t q_max, const uint32_t* ucount, const uint32_t* ulist, int fb_parts,
                               int64_t fb_rows_per_part, uint64_t* fb_cand, uint32_t* fb_cnt, uint64_t* fb_sel,
-                              float* out_scores, int64_t* out_idx, cudaStream_t st) {
+                              float* out_scores, int64_t* out_idx, uint64_t* out_packed, cudaStream_t st) {
     ScanArgs a{};
     a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
     a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist; a.nq_dev = ucount;
@@ -315,7 +323,7 @@ static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_
     RADAR_CUDA_CHECK(cudaGetLastError());
     FinalArgs g{};
     g.sel = fb_sel; g.R = k; g.k = k; g.mode = mode; g.sort = 0; g.qmap = ulist; g.nq_dev = ucount;
-    g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx;
+    g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx; g.out_packed = out_packed;
     final_kernel<<<static_cast<unsigned>(q_max), kFinalThreads, 0, st>>>(g);
     RADAR_CUDA_CHECK(cudaGetLastError());
     return RADAR_OK;
@@ -345,15 +353,37 @@ int radar_set_device(int device) {
     return RADAR_OK;
 }
 
-int radar_profile_enable(int enable) {
-    if (enable && !g_prof_start) {
-        RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_start));
-        RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_stop));
-    } else if (!enable && g_prof_start) {
+int radar_get_device(int* device) {
+    RADAR_ARG_CHECK(device, "get_device: null pointer");
+    RADAR_CUDA_CHECK(cudaGetDevice(device));
+    return RADAR_OK;
+}
+
+static void prof_destroy() {
+    if (g_prof_start) {
         cudaEventDestroy(g_prof_start);
         cudaEventDestroy(g_prof_stop);
         g_prof_start = g_prof_stop = nullptr;
+        g_prof_dev = -1;
     }
+}
+
+// the event pair lives on the device that is current when it is (re)created; radar_search re-creates it when it
+// runs on another device
+static int prof_ensure_on_current_device() {
+    int dev = 0;
+    RADAR_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_prof_start && g_prof_dev == dev) return RADAR_OK;
+    prof_destroy();
+    RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_start));
+    RADAR_CUDA_CHECK(cudaEventCreate(&g_prof_stop));
+    g_prof_dev = dev;
+    return RADAR_OK;
+}
+
+int radar_profile_enable(int enable) {
+    if (enable) return prof_ensure_on_current_device();
+    prof_destroy();
     return RADAR_OK;
 }
 
@@ -415,7 +445,7 @@ size_t radar_search_workspace_bytes(const radar_corpus_t* corpus, int64_t q, con
 }
 
 int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, const radar_search_params_t* params,
-                 float* out_scores, int64_t* out_idx, void* workspace, size_t workspace_bytes,
+                 float* out_scores, int64_t* out_idx, uint64_t* out_packed, void* workspace, size_t workspace_bytes,
                  radar_search_stats_t* stats, void* stream) {
     RADAR_ARG_CHECK(queries, "null queries");
     const int64_t q = queries->q;
@@ -430,8 +460,14 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
     DeviceInfo di;
     rc = get_device_info(&di);
     if (rc) return rc;
+    if (g_prof_start) {
+        rc = prof_ensure_on_current_device();
+        if (rc) return rc;
+    }
+    const bool search_after = queries->after_idx != nullptr;
+    RADAR_ARG_CHECK(!search_after || queries->after_scores, "queries.after_idx needs queries.after_scores");
     Plan pl;
-    rc = make_plan(corpus, q, params, di, &pl);
+    rc = make_plan(corpus, q, params, di, &pl, search_after);
     if (rc) return rc;
     if (!workspace || workspace_bytes < pl.total) {
         set_error("workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);
@@ -520,7 +556,8 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         fa.p16 = queries->p16; fa.entropy = queries->entropy; fa.logq16 = corpus->logq16; fa.qerr = qerr; fa.gthr = gthr;
         fa.gcnt = gcnt; fa.pool = pool; fa.q = static_cast<int>(q); fa.k = params->k; fa.pool_cap = pl.pool_cap;
         fa.certify = params->precision == RADAR_PREC_FP32 ? 1 : 0; fa.idx_offset = corpus->idx_offset;
-        fa.out_scores = out_scores; fa.out_idx = out_idx; fa.uncert_count = ucount; fa.uncert_list = ulist;
+        fa.out_scores = out_scores; fa.out_idx = out_idx; fa.out_packed = out_packed;
+        fa.uncert_count = ucount; fa.uncert_list = ulist;
         kls::kl_stream_final_kernel<<<static_cast<unsigned>(q), kls::kFinThreads, 0, st>>>(fa);
         RADAR_CUDA_CHECK(cudaGetLastError());
         launches += 5;
@@ -528,7 +565,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         rc = launch_exact_rerun(corpus, queries, RADAR_MODE_KL, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
                                 pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
                                 reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
-                                reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, st);
+                                reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, out_packed, st);
         if (rc) return rc;
         launches += 3;
         have_ucount = true;
@@ -538,6 +575,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = nullptr;
         a.nq = q; a.n = corpus->n; a.d = corpus->d; a.mode = params->mode; a.alpha = alpha; a.oma = oma;
         a.parts = pl.parts; a.rows_per_part = pl.rows_per_part; a.kp = pl.kp; a.cand = cand; a.cnt = cnt;
+        a.after_scores = queries->after_scores; a.after_idx = queries->after_idx; a.idx_offset = corpus->idx_offset;
         if (g_prof_start) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
         rc = launch_scan(a, pl.q_tiles, st);
         if (rc) return rc;
@@ -549,7 +587,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         ++launches;
         FinalArgs f{};
         f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 0; f.qmap = nullptr;
-        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx;
+        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx; f.out_packed = out_packed;
         final_kernel<<<static_cast<unsigned>(q), kFinalThreads, 0, st>>>(f);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
@@ -588,7 +626,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         ++launches;
         FinalArgs f{};
         f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 1; f.qmap = nullptr;
-        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx;
+        f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx; f.out_packed = out_packed;
         if (certify) {
             f.bound = bound; f.qerr = qerr; f.uncert_count = ucount; f.uncert_list = ulist;
         }
@@ -599,7 +637,8 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
             rc = launch_exact_rerun(corpus, queries, params->mode, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
                                     pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
                                     reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
-                                    reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, st);
+                                    reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, out_packed,
+                                    st);
             if (rc) return rc;
             launches += 3;
             have_ucount = true;
@@ -628,6 +667,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
     return RADAR_OK;
 }
 
+#ifdef RADAR_DEBUG
 int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t* queries,
                             const radar_search_params_t* params, float* out_keys, void* workspace,
                             size_t workspace_bytes, void* stream) {
@@ -662,6 +702,7 @@ int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t*
     int nl = 0;
     return tc::launch_filter(fl, static_cast<cudaStream_t>(stream), &nl);
 }
+#endif  // RADAR_DEBUG
 
 int radar_merge_topk(const float* cand_scores, const int64_t* cand_idx, int64_t q, int parts, int k_in, int k_out,
                      int ascending, float* out_scores, int64_t* out_idx, void* stream) {
@@ -673,6 +714,21 @@ int radar_merge_topk(const float* cand_scores, const int64_t* cand_idx, int64_t 
     if (q == 0) return RADAR_OK;
     merge_kernel<<<static_cast<unsigned>(q), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         cand_scores, cand_idx, q, parts, k_in, k_out, ascending, out_scores, out_idx);
+    RADAR_CUDA_CHECK(cudaGetLastError());
+    return RADAR_OK;
+}
+
+int radar_merge_packed(const uint64_t* cand, int64_t q, int parts, int k_in, int k_out, int mode, float* out_scores,
+                       int64_t* out_idx, void* stream) {
+    RADAR_ARG_CHECK(cand && out_scores && out_idx, "merge_packed: null pointer");
+    RADAR_ARG_CHECK(q >= 0 && parts >= 1 && k_in >= 1 && k_out >= 1, "merge_packed: bad sizes");
+    RADAR_ARG_CHECK(mode >= RADAR_MODE_DPR && mode <= RADAR_MODE_HYBRID, "merge_packed: bad mode %d", mode);
+    RADAR_ARG_CHECK(static_cast<int64_t>(parts) * k_in <= kMergeCap, "merge_packed: parts*k_in=%lld exceeds %d",
+                    (long long)parts * k_in, kMergeCap);
+    RADAR_ARG_CHECK(k_out <= parts * k_in, "merge_packed: k_out exceeds the candidate count");
+    if (q == 0) return RADAR_OK;
+    merge_packed_kernel<<<static_cast<unsigned>(q), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        cand, q, parts, k_in, k_out, mode, out_scores, out_idx);
     RADAR_CUDA_CHECK(cudaGetLastError());
     return RADAR_OK;
 }

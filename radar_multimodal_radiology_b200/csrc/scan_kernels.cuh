@@ -43,10 +43,15 @@ struct ScanArgs {
     int kp;                 // entries kept by a compaction (= k on this exact path)
     uint64_t* cand;         // [nq][parts][kCandCap]
     uint32_t* cnt;          // [nq][parts]
+    // "search after" (radar_queries_t::after_*, nullable): only cases ranking strictly after (score, id) are kept
+    const float* after_scores;
+    const int64_t* after_idx;
+    int64_t idx_offset;
 };
 
 constexpr size_t kScanSmemBytes =
-    sizeof(float) * (2 * kScanKC * kScanLd + 2 * kObsPad * kScanTQ + 2 * kScanTQ) + sizeof(uint32_t) * 2 * kScanTQ;
+    sizeof(float) * (2 * kScanKC * kScanLd + 2 * kObsPad * kScanTQ + 2 * kScanTQ) + sizeof(uint32_t) * 3 * kScanTQ +
+    sizeof(long long) * kScanTQ;
 
 // warp-cooperative compaction of one candidate buffer (n <= kCandCap composites in global memory, written by lanes
 // of this warp before a __syncwarp): keep exactly the best kp, return the kp-th key.  Selection, not sorting: the
@@ -122,6 +127,8 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
     float* thr = Hs + kScanTQ;                       // [TQ]
     uint32_t* cnt_s = reinterpret_cast<uint32_t*>(thr + kScanTQ);  // [TQ]
     uint32_t* qid_s = cnt_s + kScanTQ;                             // [TQ]
+    uint32_t* ubk_s = qid_s + kScanTQ;                             // [TQ] search-after bound: orderable key bits
+    long long* ubr_s = reinterpret_cast<long long*>(ubk_s + kScanTQ);  // [TQ] ... and LOCAL row (may lie outside the shard)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -141,6 +148,13 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
         thr[tid] = -CUDART_INF_F;
         cnt_s[tid] = 0;
         Hs[tid] = (valid && HAS_KL) ? a.entropy[qid] : 0.0f;
+        ubk_s[tid] = 0xFFFFFFFFu;   // no bound: every finite key orders below it
+        ubr_s[tid] = -1;
+        if (valid && a.after_idx && a.after_idx[qid] >= 0) {
+            const float sc = a.after_scores[qid];
+            ubk_s[tid] = f2ord(a.mode == RADAR_MODE_KL ? __fsub_rn(0.0f, sc) : sc);
+            ubr_s[tid] = a.after_idx[qid] - a.idx_offset;
+        }
 #pragma unroll
         for (int j = 0; j < kObsPad; ++j)
             Ps[j * kScanTQ + tid] = (valid && HAS_KL) ? a.p16[static_cast<int64_t>(qid) * kObsPad + j] : 0.0f;
@@ -234,8 +248,12 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
                 const int64_t row = row0 + tx * 4 + j;
                 const float key = canonical_key(a.mode, ip[i][j], x[i][j], h, a.alpha, a.oma);
                 if (row < part_end && key >= t) {
-                    const uint32_t slot = atomicAdd(&cnt_s[ql], 1u);
-                    buf[slot] = make_composite(key, static_cast<uint32_t>(row));
+                    // search-after: drop what ranks at or before the bound (better key, or equal key and id <= bound id)
+                    const uint32_t o = f2ord(key), ub = ubk_s[ql];
+                    if (o < ub || (o == ub && row > ubr_s[ql])) {
+                        const uint32_t slot = atomicAdd(&cnt_s[ql], 1u);
+                        buf[slot] = make_composite(key, static_cast<uint32_t>(row));
+                    }
                 }
             }
         }
@@ -419,6 +437,7 @@ struct FinalArgs {
     int64_t idx_offset;
     float* out_scores;
     int64_t* out_idx;
+    uint64_t* out_packed;  // nullable: (key bits << 32) | (0xFFFFFFFF - global id), 0 = padding
     // certificate (all nullable)
     const float* bound;
     const float* qerr;
@@ -452,6 +471,7 @@ __global__ void __launch_bounds__(kFinalThreads) final_kernel(const FinalArgs a)
         }
         a.out_scores[qid * a.k + j] = sc;
         a.out_idx[qid * a.k + j] = id;
+        if (a.out_packed) a.out_packed[qid * a.k + j] = c != 0ull ? packed_global(c, a.idx_offset) : 0ull;
     }
     if (a.bound && tid == 0) {
         const float b = a.bound[qi];
@@ -502,6 +522,36 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ sc
             out_idx[qi * k_out + j] = static_cast<int64_t>(composite_row(c));
         } else {
             out_scores[qi * k_out + j] = ascending ? CUDART_INF_F : -CUDART_INF_F;
+            out_idx[qi * k_out + j] = -1;
+        }
+    }
+}
+
+// the same merge on packed words (radar_search's out_packed; one 8-byte all-gather instead of scores + ids)
+__global__ void __launch_bounds__(256) merge_packed_kernel(const uint64_t* __restrict__ cand, int64_t nq, int parts,
+                                                           int k_in, int k_out, int mode, float* __restrict__ out_scores,
+                                                           int64_t* __restrict__ out_idx) {
+    __shared__ uint64_t s[kMergeCap];
+    const int64_t qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int total = parts * k_in;
+    const int P = max(next_pow2(total), 2);
+    for (int i = tid; i < P; i += 256) {
+        uint64_t c = 0ull;
+        if (i < total) {
+            const int p = i / k_in, j = i - p * k_in;
+            c = cand[(static_cast<int64_t>(p) * nq + qi) * k_in + j];
+        }
+        s[i] = c;
+    }
+    bitonic_sort_desc(s, P, tid, 256, [] { __syncthreads(); });
+    for (int j = tid; j < k_out; j += 256) {
+        const uint64_t c = s[j];
+        if (c != 0ull) {
+            out_scores[qi * k_out + j] = api_score_from_key(mode, composite_key(c));
+            out_idx[qi * k_out + j] = static_cast<int64_t>(composite_row(c));
+        } else {
+            out_scores[qi * k_out + j] = mode == RADAR_MODE_KL ? CUDART_INF_F : -CUDART_INF_F;
             out_idx[qi * k_out + j] = -1;
         }
     }

@@ -36,6 +36,15 @@
 namespace radar {
 namespace tc {
 
+// Bring-up / measurement hooks (dense key dump, epilogue and TMA knock-outs, window switch) exist only in the
+// RADAR_DEBUG flavour of the library (libradar_retrieval_dbg.so, built for the tests); in the release build the
+// expressions below are the constant 0 and the code behind them is removed by the compiler.
+#ifdef RADAR_DEBUG
+#define RADAR_DBG(expr) (expr)
+#else
+#define RADAR_DBG(expr) (0)
+#endif
+
 constexpr int kBlockM = 128;          // query rows per CTA == TMEM lanes
 constexpr int kTileQ = 2 * kBlockM;   // query rows per work tile (CTA pair)
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue (+ warps 6..9 in KL mode)
@@ -265,7 +274,7 @@ struct FilterArgs {
                         // query tile that run later start from it instead of -inf
     unsigned long long* progress;  // [units] (round << 32 | tiles loaded) of every pair; zeroed before the launch
     int window;         // tiles a pair may run ahead of the slowest pair sweeping the same slab (0 = unbounded)
-    float* dbg_scores;  // optional [q_pad][n] dense dump of the filter keys (bring-up / tests only)
+    float* dbg_scores;  // RADAR_DEBUG builds only: optional [q_pad][n] dense dump of the filter keys
     // KL threshold prepass (see launch_filter): prepass = 1 -> the epilogue only records, per query, the maximum key of every
     // group of `group_tiles` consecutive sampled tiles of a slab (groupmax[qrow][slab][group], ord-encoded); the k'-th largest
     // group maximum is then a near-exact initial threshold for the real pass (gthr_init = 1), which so sees ~k' survivors
@@ -274,7 +283,7 @@ struct FilterArgs {
     int prepass, gthr_init, group_tiles, groups, groups_per_slab;
     int tile_stride;    // 1, or > 1 in the prepass: only every tile_stride-th tile of a slab is visited (a sample still
                         // yields a valid, slightly looser threshold at 1/tile_stride of the cost)
-    int dbg_flags;      // measurement aid (RADAR_TC_DBG, results are garbage): 1 = epilogue only recycles the
+    int dbg_flags;      // RADAR_DEBUG builds only (env RADAR_TC_DBG, results are garbage): 1 = epilogue only recycles the
                         // accumulators, 2 = no TMA loads (MMAs run on whatever is in shared memory), 4 = epilogue
                         // loads the accumulators but does not look at them
     unsigned long long* clk;  // [2] SM cycles / nanoseconds CTA 0 spent in the kernel (average SM clock of the launch)
@@ -455,7 +464,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     }
                 }
                 mbar_wait(&empty_bar[slot], sph ^ 1);
-                if (a.dbg_flags & 2) {
+                if (RADAR_DBG(a.dbg_flags & 2)) {
                     if (leader && lane == 0)
                         for (int g = 0; g < groups; ++g) mbar_arrive(&full_bar[slot * kMaxGroups + g]);
                 } else if (elect_one()) {
@@ -619,7 +628,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                 // occasional candidate insertions / compactions) overlaps the next tile's MMAs instead of sitting
                 // between two of them.
                 float v[COLS];
-                if (!(a.dbg_flags & 1)) {
+                if (!RADAR_DBG(a.dbg_flags & 1)) {
 #pragma unroll
                     for (int c = 0; c < COLS; c += 32) {
                         if (COLS - c >= 32) tmem_ld_x32(t_acc + c, v + c);
@@ -634,8 +643,8 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     as = 0;
                     aph ^= 1;
                 }
-                if (a.dbg_flags & 5) {
-                    if (a.dbg_flags & 4) asm volatile("" ::"f"(v[0]), "f"(v[COLS - 1]));
+                if (RADAR_DBG(a.dbg_flags & 5)) {
+                    if (RADAR_DBG(a.dbg_flags & 4)) asm volatile("" ::"f"(v[0]), "f"(v[COLS - 1]));
                     continue;
                 }
                 if (a.prepass) {
@@ -672,7 +681,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                     for (int jj = 4; jj < 32; ++jj)
                         if (jj < width) mm[jj & 3] = fmaxf(mm[jj & 3], v[c + jj]);
                     const float m = fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
-                    if (__any_sync(0xffffffffu, m >= thr_cmp) || a.dbg_scores) {
+                    if (__any_sync(0xffffffffu, m >= thr_cmp) || RADAR_DBG(a.dbg_scores != nullptr)) {
                         // rare path, written for a small instruction footprint (it used to be unrolled per column and
                         // pushed the kernel far beyond the instruction cache): the chunk is staged in this warp's
                         // shared-memory scratch together with a survivor bit mask, then a short loop walks the set bits
@@ -684,7 +693,7 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                                 mask |= (v[c + jj] >= thr_cmp ? 1u : 0u) << jj;
                             }
                         }
-                        if (a.dbg_scores && valid) {
+                        if (RADAR_DBG(a.dbg_scores != nullptr) && valid) {
                             for (int jj = 0; jj < width; ++jj)
                                 if (rowc + c + jj < a.n) a.dbg_scores[qrow * a.n + rowc + c + jj] = my_stage[jj * 32] - shift;
                         }
@@ -903,7 +912,9 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     fa.apack = fl.apack; fa.qshift = qshift; fa.q = fl.q; fa.q_tiles = fl.q_tiles; fa.n = fl.corpus->n;
     fa.d = fl.corpus->d; fa.parts = fl.parts; fa.rows_per_part = fl.rows_per_part; fa.kp = fl.kp;
     fa.cand = fl.cand; fa.cnt = fl.cnt; fa.thr = fl.thr; fa.gthr = fl.gthr; fa.dbg_scores = fl.dbg_scores;
+#ifdef RADAR_DEBUG
     fa.dbg_flags = getenv("RADAR_TC_DBG") ? atoi(getenv("RADAR_TC_DBG")) : 0;
+#endif
     fa.tile_stride = 1;
     fa.progress = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(fl.gthr) +
                                                         (sizeof(uint32_t) * static_cast<size_t>(q_pad) + 7) / 8 * 8);
@@ -916,7 +927,10 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
     int64_t window = (16ll << 20) / tile_bytes;
     if (window < 4 * kProgressEvery) window = 4 * kProgressEvery;
     const bool resident = 2 * fl.units <= fl.device_sms;
-    fa.window = (resident && fl.q_tiles > 1 && getenv("RADAR_TC_NO_WINDOW") == nullptr) ? static_cast<int>(window) : 0;
+    fa.window = (resident && fl.q_tiles > 1) ? static_cast<int>(window) : 0;
+#ifdef RADAR_DEBUG
+    if (getenv("RADAR_TC_NO_WINDOW") != nullptr) fa.window = 0;
+#endif
     int rc;
     const bool d512 = fl.corpus->d == 512;
     *launches = 2;
@@ -926,10 +940,13 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
         FilterArgs fp = fa;
         fp.prepass = 1; fp.groupmax = fl.groupmax; fp.groups = fl.groups; fp.group_tiles = fl.group_tiles;
         fp.tile_stride = fl.tile_stride; fp.groups_per_slab = fl.groups_per_slab;
-        cudaEvent_t e0 = fl.ev_start, e1 = fl.ev_stop;
-        fl.ev_start = fl.ev_stop = nullptr;  // the profiled kernel is the real pass
+        // the profiled span covers the prepass, the threshold selection and the real pass: start event before the
+        // prepass, stop event after the real pass
+        cudaEvent_t e1 = fl.ev_stop;
+        fl.ev_stop = nullptr;
         rc = launch_filter_mode<RADAR_MODE_KL, 0>(fl, fp, st);
-        fl.ev_start = e0; fl.ev_stop = e1;
+        fl.ev_start = nullptr;
+        fl.ev_stop = e1;
         if (rc) return rc;
         group_threshold_kernel<<<static_cast<unsigned>((fl.q * 32 + 255) / 256), 256, 0, st>>>(fl.groupmax, fl.q, fl.groups,
                                                                                                  fl.kp, fl.gthr);

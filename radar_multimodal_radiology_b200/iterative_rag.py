@@ -215,9 +215,9 @@ def rerank_overlap(case_bits: torch.Tensor, missing_bits: torch.Tensor) -> Tuple
     q, k = cb.shape
     scores = torch.empty((q, k), dtype=torch.float64, device=cb.device)
     order = torch.empty((q, k), dtype=torch.int32, device=cb.device)
-    L.set_device(cb.device)
-    L.check(L.lib().radar_rerank_overlap(L.ptr(cb), L.ptr(mb), q, k, L.ptr(scores), L.ptr(order),
-                                         L.current_stream_ptr(cb.device)), "radar_rerank_overlap")
+    with L.device_guard(cb.device):
+        L.check(L.lib().radar_rerank_overlap(L.ptr(cb), L.ptr(mb), q, k, L.ptr(scores), L.ptr(order),
+                                             L.current_stream_ptr(cb.device)), "radar_rerank_overlap")
     return scores, order
 
 
@@ -226,9 +226,9 @@ def gather_case_bits(table: torch.Tensor, ids: torch.Tensor, idx_offset: int = 0
     t = table.contiguous().to(torch.int16)
     ids = ids.contiguous()
     out = torch.empty(ids.shape, dtype=torch.int16, device=ids.device)
-    L.set_device(ids.device)
-    L.check(L.lib().radar_gather_bits(L.ptr(t), t.shape[0], L.ptr(ids), ids.shape[0], ids.shape[1], idx_offset,
-                                      L.ptr(out), L.current_stream_ptr(ids.device)), "radar_gather_bits")
+    with L.device_guard(ids.device):
+        L.check(L.lib().radar_gather_bits(L.ptr(t), t.shape[0], L.ptr(ids), ids.shape[0], ids.shape[1], idx_offset,
+                                          L.ptr(out), L.current_stream_ptr(ids.device)), "radar_gather_bits")
     return out
 
 

@@ -646,3 +646,138 @@ def test_graphed_search_replay_equals_eager(dev, mode, n, q):
     p_new = dict(p, q_pr=p2["q_pr"], q_emb=p2["q_emb"])
     ws, wi = _oracle(p_new, mode, 10)
     assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+
+
+# ---------------------------------------------------------------------------------------------------
+# round 2: packed exchange words, k > RADAR_MAX_K paging, graph lifetime, device hygiene, add() copies
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+@pytest.mark.parametrize("algo,precision", [("simt", "fp32"), ("tc", "fp32"), ("tc", "bf16")])
+def test_packed_output_is_the_same_result_as_scores_and_ids(dev, mode, algo, precision):
+    from oracle import c_oracle as co
+    p = make_problem(7001, 130, seed=61)
+    idx = _index(p, dev, precision=precision, algo=algo, idx_offset=4_000_000_000 - 7001 - 5)  # ids near 2^32
+    xq = None if mode == "kl" else torch.from_numpy(p["q_emb"]).to(dev)
+    s, i, w = idx.search(xq, 10, query_probs=p["q_pr"], mask=p["mask"], mode=mode, return_packed=True)
+    s, i, w = s.cpu().numpy(), i.cpu().numpy(), w.cpu().numpy()
+    assert np.array_equal(w, co.pack_results(_MODES[mode], s, i))
+    ms, mi = co.merge_packed(w[None], 10, _MODES[mode])
+    assert np.array_equal(mi, i) and np.array_equal(ms, s)
+
+
+_MODES = {"dpr": 0, "kl": 1, "hybrid": 2}
+
+
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+@pytest.mark.parametrize("world", [2, 8])
+def test_packed_shard_merge_equals_single_shard(dev, mode, world):
+    """Row shards searched one after another on one GPU, exchanged as packed words, merged by merge_packed_kernel
+    == the unsharded canonical result (the data path of ShardedRadarIndex without the collective)."""
+    from radar_multimodal_radiology_b200.index import RadarIndex, merge_packed
+    from radar_multimodal_radiology_b200.sharded import shard_bounds
+    n = 10007
+    p = make_problem(n, 200, seed=14)
+    k = 32
+    ws, wi = _oracle(p, mode, k)
+    words = []
+    for r in range(world):
+        lo, hi = shard_bounds(n, world, r)
+        idx = RadarIndex(512, device=dev, precision="fp32", idx_offset=lo)
+        idx.add(p["c_emb"][lo:hi])
+        idx.add_observations(p["c_pr"][lo:hi])
+        xq = None if mode == "kl" else p["q_emb"]
+        words.append(idx.search(xq, k, query_probs=p["q_pr"], mask=p["mask"], mode=mode, return_packed=True)[2])
+    ms, mi = merge_packed(torch.stack(words), k, mode)
+    assert np.array_equal(mi.cpu().numpy(), wi) and np.array_equal(ms.cpu().numpy(), ws)
+
+
+def test_merge_packed_kernel_matches_oracle_with_ties_and_padding(dev):
+    from oracle import c_oracle as co
+    from radar_multimodal_radiology_b200.index import merge_packed
+    rng = np.random.default_rng(5)
+    parts, q, k_in = 8, 257, 32
+    s = np.round(rng.standard_normal((parts, q, k_in)), 1).astype(np.float32)  # plenty of cross-shard ties
+    i = rng.permutation(parts * q * k_in).reshape(parts, q, k_in).astype(np.int64)
+    i[0, :, -3:] = -1
+    for mode in (0, 1, 2):
+        w = np.stack([co.pack_results(mode, s[g], i[g]) for g in range(parts)])
+        ws, wi = co.merge_packed(w, 20, mode)
+        gs, gi = merge_packed(torch.from_numpy(w).to(dev), 20, ["dpr", "kl", "hybrid"][mode])
+        assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gs.cpu().numpy(), ws)
+
+
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+@pytest.mark.parametrize("k", [129, 300, 1000])
+def test_k_beyond_max_k_pages_through_the_exact_ranking(dev, mode, k):
+    """faiss accepts any k (dpr.py:313; retrieve_with_hard_negatives asks for k + num_negatives): k > RADAR_MAX_K
+    is served by paging (radar_queries.after_*) and equals the oracle's top-k, duplicates and ties included."""
+    p = make_problem(1500, 40, seed=62)
+    p["c_emb"][700:720] = p["c_emb"][100]  # 21 exact duplicates straddle page boundaries for some queries
+    p["c_pr"][700:720] = p["c_pr"][100]
+    ws, wi = _oracle(p, mode, k)
+    idx = _index(p, dev, precision="fp32")
+    s, i = _search(idx, p, mode, k)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    with pytest.raises(ValueError, match="exact scan"):
+        _search(idx, p, mode, k, algo="tc")
+
+
+def test_hybrid_retriever_accepts_k_above_128(dev):
+    from radar_multimodal_radiology_b200.dense_passage_retrieval import HybridRetriever, RetrievalConfig
+    n = 400
+    p = make_problem(n, 2, seed=63)
+    r = HybridRetriever(RetrievalConfig(), embedder=None)
+    r.build_indices([f"case {j}" for j in range(n)], [], embeddings=torch.from_numpy(p["c_emb"]).to(dev))
+    passages, scores = r.retrieve(torch.from_numpy(p["q_emb"][0]).to(dev), k=250)
+    assert len(passages) == 250 and scores == sorted(scores, reverse=True)
+    out = r.retrieve_with_hard_negatives(torch.from_numpy(p["q_emb"][0]).to(dev), k=127, num_negatives=3)
+    assert len(out["positives"]) == 127 and len(out["negatives"]) == 3
+
+
+def test_graphed_search_refuses_to_replay_after_the_index_changed(dev):
+    from radar_multimodal_radiology_b200.index import GraphedSearch
+    p = make_problem(20000, 64, seed=64)
+    idx = _index(p, dev, precision="fp32")
+    xq = torch.from_numpy(p["q_emb"]).to(dev)
+    pr = torch.from_numpy(p["q_pr"]).to(dev)
+    g = GraphedSearch(idx, xq, 10, query_probs=pr, alpha=0.5, mode="hybrid")
+    ws, wi = _oracle(p, "hybrid", 10, masked=False)
+    # an eager search that needs a much larger workspace must not disturb the captured one (private workspace)
+    big = make_problem(20000, 3000, seed=65)
+    idx.search(torch.from_numpy(big["q_emb"]).to(dev), 10, query_probs=big["q_pr"], mode="hybrid")
+    s, i = g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(s.cpu().numpy(), ws)
+    idx.add(p["c_emb"][:10])
+    idx.add_observations(p["c_pr"][:10])
+    with pytest.raises(RuntimeError, match="index changed"):
+        g.replay()
+
+
+def test_add_copies_its_input_like_faiss(dev):
+    p = make_problem(3000, 50, seed=66)
+    from radar_multimodal_radiology_b200.index import RadarIndex
+    idx = RadarIndex(512, device=dev, precision="fp32")
+    buf = torch.from_numpy(p["c_emb"]).to(dev)
+    for lo in range(0, 3000, 700):  # several adds: the stores grow geometrically, rows stay in insertion order
+        idx.add(buf[lo:lo + 700])
+        idx.add_observations(p["c_pr"][lo:lo + 700])
+    buf.zero_()  # the caller reuses its buffer
+    torch.cuda.synchronize()
+    ws, wi = _oracle(p, "hybrid", 10)
+    s, i = _search(idx, p, "hybrid", 10)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    assert idx.ntotal == 3000 and idx.emb_bf16.shape[0] == 3000
+
+
+def test_library_calls_restore_the_current_device(dev):
+    from radar_multimodal_radiology_b200 import _lib
+    import ctypes
+    before = ctypes.c_int(-1)
+    _lib.lib().radar_get_device(ctypes.byref(before))
+    p = make_problem(2000, 10, seed=67)
+    idx = _index(p, dev)
+    _search(idx, p, "hybrid", 5)
+    after = ctypes.c_int(-1)
+    _lib.lib().radar_get_device(ctypes.byref(after))
+    assert before.value == after.value and torch.cuda.current_device() == before.value

@@ -11,18 +11,40 @@ import pytest
 from conftest import ROOT
 
 
+def _declared(header: str):
+    return set(re.findall(r"^\s*(?:const char\*|int|size_t)\s+(radar_[a-z0-9_]+)\s*\(", header, re.M))
+
+
+def _exported(path: str):
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    return set(re.findall(r" T (radar_[a-z0-9_]+)", out))
+
+
 def test_abi_library_loads_and_exports_every_declared_symbol(built_lib):
     from radar_multimodal_radiology_b200 import _lib
     header = open(_lib.HEADER_PATH).read()
-    declared = set(re.findall(r"^\s*(?:const char\*|int|size_t)\s+(radar_[a-z0-9_]+)\s*\(", header, re.M))
+    # the part of the header guarded by RADAR_DEBUG belongs to the debug flavour of the library only
+    release_header = re.sub(r"#ifdef RADAR_DEBUG.*?#endif", "", header, flags=re.S)
+    declared, declared_dbg = _declared(release_header), _declared(header)
     assert declared, "no declarations parsed from the header"
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert declared_dbg - declared == set(_lib.DEBUG_EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), f"{name} not exported"
-    assert built_lib.radar_abi_version() == 2
-    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    exported = set(re.findall(r" T (radar_[a-z0-9_]+)", out))
-    assert declared <= exported
+    assert built_lib.radar_abi_version() == _lib.ABI_VERSION == 3
+    assert _exported(_lib.LIB_PATH) == declared            # nothing undeclared leaks out of the release library
+    assert _exported(_lib.DBG_LIB_PATH) == declared_dbg
+    dbg = _lib.debug_lib()
+    assert dbg.radar_abi_version() == 3 and hasattr(dbg, "radar_debug_filter_keys")
+
+
+def test_release_library_reads_no_environment_variables():
+    """a stray RADAR_TC_DBG must not be able to change what radar_search returns."""
+    from radar_multimodal_radiology_b200 import _lib
+    strings = subprocess.run(["strings", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "RADAR_TC_DBG" not in strings and "RADAR_TC_NO_WINDOW" not in strings
+    dbg = subprocess.run(["strings", _lib.DBG_LIB_PATH], capture_output=True, text=True).stdout
+    assert "RADAR_TC_DBG" in dbg
 
 
 def test_library_is_built_for_sm_100a_with_tensor_core_and_tma_instructions(built_lib):

@@ -1,5 +1,5 @@
 """CPU, world_size 2 over gloo: the multi-GPU host logic (row partition, short-shard padding, all-gather
-layout, global ids, merge order).  The local search and the merge are injected from the oracle -- in the
+layout of the packed result words, global ids, merge order, sliced query upload).  The local search and the merge are injected from the oracle -- in the
 product they are the CUDA kernels (tests/test_gpu_parity.py covers those); nothing here is a product
 fallback."""
 import os
@@ -29,15 +29,16 @@ def _worker(rank, world, port, n, q, k, mode_name, out_dir):
     lo, hi = shard_bounds(n, world, rank)
     logq = co.prepare_corpus(p["c_pr"][lo:hi]) if hi > lo else np.zeros((0, 16), np.float32)
 
-    def local_search(x, kk, query_probs=None, mask=None, alpha=0.5, mode=None, **kw):
+    def local_search(x, kk, query_probs=None, mask=None, alpha=0.5, mode=None, return_packed=False, **kw):
         p16, ent = co.prepare_queries(query_probs.numpy(), None if mask is None else mask.numpy())
         m = {"dpr": 0, "kl": 1, "hybrid": 2}[mode]
         s, i = co.search(m, kk, q_emb=None if x is None else x.numpy(), p16=p16, entropy=ent,
                          c_emb=p["c_emb"][lo:hi], logq16=logq, alpha=alpha, idx_offset=lo)
-        return torch.from_numpy(s), torch.from_numpy(i)
+        out = (torch.from_numpy(s), torch.from_numpy(i))
+        return out + (torch.from_numpy(co.pack_results(m, s, i)),) if return_packed else out
 
-    def merge(gs, gi, kk, ascending):
-        s, i = co.merge_topk(gs.numpy(), gi.numpy(), kk, ascending)
+    def merge(packed, kk, mode):
+        s, i = co.merge_packed(packed.numpy(), kk, {"dpr": 0, "kl": 1, "hybrid": 2}[mode])
         return torch.from_numpy(s), torch.from_numpy(i)
 
     idx = ShardedRadarIndex(512, device="cpu", local_search=local_search, merge=merge).build(n)
@@ -45,6 +46,10 @@ def _worker(rank, world, port, n, q, k, mode_name, out_dir):
     x = None if mode_name == "kl" else torch.from_numpy(p["q_emb"])
     s, i = idx.search(x, k, query_probs=torch.from_numpy(p["q_pr"]), mask=torch.from_numpy(p["mask"]), alpha=0.5,
                       mode=mode_name)
+    # host-resident queries: every rank uploads its 1/G slice, the slices are all-gathered (ragged last slice)
+    host = torch.arange(q * 3, dtype=torch.float32).reshape(q, 3)
+    up = idx.upload_queries(host)
+    assert up.shape == host.shape and torch.equal(up, host)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), s=s.numpy(), i=i.numpy())
     dist.barrier()
     dist.destroy_process_group()
