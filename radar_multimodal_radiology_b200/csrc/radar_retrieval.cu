@@ -84,6 +84,15 @@ static int auto_overfetch(int k) {
     return kp;
 }
 
+// KL keys come out of the filter almost exactly (bf16 hi/lo split of both operands: ~1e-4 relative), so a handful of
+// spare candidates is enough; fewer candidates = tighter thresholds = fewer survivors through the filter's rare path
+static int auto_overfetch_kl(int k) {
+    int kp = (k + 6 + 7) / 8 * 8;
+    if (kp < 16) kp = 16;
+    if (kp > kCandSoft) kp = kCandSoft;
+    return kp;
+}
+
 static bool tc_supported(const radar_corpus_t* c, int mode, const DeviceInfo& di) {
     if (di.major != 10) return false;
     if (mode != RADAR_MODE_KL) {
@@ -176,7 +185,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         return o;
     };
     if (algo == RADAR_ALGO_KL_STREAM) {
-        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch(p->k);
+        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl(p->k);
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
@@ -215,7 +224,8 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->q_tiles = ceil_div64(q, kScanTQ);
         plan_parts(pl->q_tiles, c->n, kScanTC, sms, 2, &pl->parts, &pl->rows_per_part);
     } else {
-        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch(p->k);
+        pl->kp = p->overfetch > 0 ? p->overfetch
+                                  : (p->mode == RADAR_MODE_KL ? auto_overfetch_kl(p->k) : auto_overfetch(p->k));
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
@@ -245,7 +255,10 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         // near-exact thresholds.  Groups: about 384 per query, at least 4 k'.
         if (p->mode == RADAR_MODE_KL && c->n <= (2ll << 20) && pl->q_tiles >= 8) {
             const int64_t c_tiles = ceil_div64(c->n, tc::block_n_for_mode(RADAR_MODE_KL));
-            int64_t stride = c_tiles / 768;  // the prepass visits ~768-1500 sampled tiles per slab sweep
+#ifndef RADAR_KL_PREPASS_TILES
+#define RADAR_KL_PREPASS_TILES 768
+#endif
+            int64_t stride = c_tiles / RADAR_KL_PREPASS_TILES;  // the prepass visits about that many sampled tiles (up to 2x)
             if (stride < 1) stride = 1;
             // groups are formed per slab (a slab's sampled tiles are numbered from the slab start), so bound them per slab
             const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, tc::block_n_for_mode(RADAR_MODE_KL)), stride);

@@ -50,22 +50,61 @@ constexpr int kTileQ = 2 * kBlockM;   // query rows per work tile (CTA pair)
 constexpr int kThreads = 192;         // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue (+ warps 6..9 in KL mode)
 constexpr int kTmemCols = 512;
 constexpr int kAIpCols = 256;         // TMEM columns reserved for the embedding part of A (d <= 512)
-constexpr int kRingBytes = 192 * 1024;  // shared-memory ring of tile slots (per CTA)
-constexpr int kMaxSlots = 8;
+constexpr int kRingBytes = 192 * 1024;  // shared-memory ring of tile slots (per CTA); KL tiles are small: 96 KB there
+constexpr int kMaxSlots = 16;
 constexpr int kMaxGroups = 4;         // full barriers per slot: one per two K-blocks
 constexpr int kMaxUnits = 1024;       // CTA pairs a launch may use (progress words in the workspace)
 constexpr int kProgressEvery = 8;     // tiles between progress publications / window checks
 constexpr uint32_t kSpinLimit = 1u << 27;
 constexpr uint32_t kWindowSpinLimit = 1u << 16;  // polls (x ~1 us) before a pair stops honouring the window
 
-__host__ __device__ constexpr int block_n_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? 112 : 128; }
-__host__ __device__ constexpr int acc_stages_for_mode(int mode) { return mode == RADAR_MODE_KL ? 3 : 2; }
-// Epilogue warp sets.  A KL tile is three K = 16 MMAs, so in KL mode the threshold filter -- not the tensor pipe -- is the
-// bound: two sets of four warps split every tile's columns (each set keeps its own candidate buffers and thresholds).
-__host__ __device__ constexpr int epi_sets_for_mode(int mode) { return mode == RADAR_MODE_KL ? 2 : 1; }
+// KL mode geometry.  A KL tile is three K = 16 MMAs (~80 cycles each at N = 160), so there the bound is not the tensor
+// pipe but (a) how long an accumulator stage stays occupied -- commit -> mbarrier -> tcgen05.ld -> remote arrive is ~1000
+// cycles, of which reading the stage back is the part that can be shortened -- and (b) the threshold filter itself.
+// Measured (tools/micro/ldtm_bw.cu): a tcgen05.wait::ld after every single load caps TMEM reads at ~128 B/cycle/SM;
+// two loads per wait and 3-4 warps per lane quadrant reach ~470 B/cycle/SM.  Hence:
+//   * kKlStages accumulator stages of kKlBlockN columns (as much of the 512 TMEM columns as possible in flight);
+//   * the epilogue warp sets (four warps each, one per lane quadrant) form kKlTileStreams x kKlColSplit: tile g of a
+//     pair is filtered by the kKlColSplit sets of stream g mod kKlTileStreams, each reading its own column range with
+//     two tcgen05.ld per wait -- a stage is read back by several warps at once (short occupancy) while other streams
+//     are still filtering the previous tiles (no warp sits in the hand-off chain of every tile).
+#ifndef RADAR_KL_BLOCK_N
+#define RADAR_KL_BLOCK_N 160
+#endif
+#ifndef RADAR_KL_STAGES
+#define RADAR_KL_STAGES 3
+#endif
+#ifndef RADAR_KL_TILE_STREAMS
+#define RADAR_KL_TILE_STREAMS 3
+#endif
+#ifndef RADAR_KL_COL_SPLIT
+#define RADAR_KL_COL_SPLIT 1
+#endif
+constexpr int kKlBlockN = RADAR_KL_BLOCK_N;
+constexpr int kKlStages = RADAR_KL_STAGES;
+constexpr int kKlTileStreams = RADAR_KL_TILE_STREAMS;
+constexpr int kKlColSplit = RADAR_KL_COL_SPLIT;
+constexpr int kKlSets = kKlTileStreams * kKlColSplit;
+constexpr int kKlAccCol0 = 32;        // the packed [v_hi | v_lo] query rows occupy TMEM columns 0..15
+static_assert(kKlBlockN % 16 == 0 && kKlBlockN >= 32 && kKlBlockN <= 256, "KL tile width");
+static_assert((kKlBlockN / kKlColSplit) % 16 == 0 && kKlBlockN % kKlColSplit == 0, "KL column split");
+static_assert(kKlAccCol0 + kKlStages * kKlBlockN <= 512, "KL accumulator stages exceed TMEM");
+static_assert(kKlSets >= 1 && kKlSets <= 5 && kKlStages <= 8, "KL warp sets");
+// a stream waits for "its" tile on an mbarrier PARITY: it must not get two phases ahead of the barrier, which holds
+// because the tiles complete in order and a stream that is done with tile g - TS knows tile g - STAGES is complete
+static_assert(kKlTileStreams <= kKlStages, "KL tile streams may not outnumber the accumulator stages");
+
+__host__ __device__ constexpr int block_n_for_mode(int mode) {
+    return mode == RADAR_MODE_HYBRID ? 112 : (mode == RADAR_MODE_KL ? kKlBlockN : 128);
+}
+__host__ __device__ constexpr int acc_stages_for_mode(int mode) { return mode == RADAR_MODE_KL ? kKlStages : 2; }
+// Epilogue warp sets (four warps each, one per TMEM lane quadrant).  DPR / hybrid: one set (the tensor pipe is the bound).
+// KL: tile streams x column splits (above); every set keeps its own candidate buffers and thresholds (select_kernel
+// merges them; the sets of a CTA share their best thresholds through shared memory).
+__host__ __device__ constexpr int epi_sets_for_mode(int mode) { return mode == RADAR_MODE_KL ? kKlSets : 1; }
 __host__ __device__ constexpr int threads_for_mode(int mode) { return 64 + 128 * epi_sets_for_mode(mode); }
 __host__ __device__ constexpr int acc_col0_for_mode(int mode) {
-    return mode == RADAR_MODE_DPR ? kAIpCols : (mode == RADAR_MODE_HYBRID ? kAIpCols + 32 : 128);
+    return mode == RADAR_MODE_DPR ? kAIpCols : (mode == RADAR_MODE_HYBRID ? kAIpCols + 32 : kKlAccCol0);
 }
 __host__ __device__ constexpr int a_kl_col_for_mode(int mode) { return mode == RADAR_MODE_HYBRID ? kAIpCols : 0; }
 // bf16 elements per packed query row
@@ -78,15 +117,22 @@ __host__ __device__ constexpr int sub_kl_bytes(int mode) { return block_n_for_mo
 __host__ __device__ constexpr int slot_stride_for(int mode, int kblocks) {
     return (kblocks * sub_ip_bytes(mode) + (mode != RADAR_MODE_DPR ? sub_kl_bytes(mode) : 0) + 1023) / 1024 * 1024;
 }
+__host__ __device__ constexpr int ring_bytes_for(int mode) { return mode == RADAR_MODE_KL ? 96 * 1024 : kRingBytes; }
 __host__ __device__ constexpr int slots_for(int mode, int kblocks) {
-    return kRingBytes / slot_stride_for(mode, kblocks) > kMaxSlots ? kMaxSlots
-                                                                  : kRingBytes / slot_stride_for(mode, kblocks);
+    return ring_bytes_for(mode) / slot_stride_for(mode, kblocks) > kMaxSlots
+               ? kMaxSlots
+               : ring_bytes_for(mode) / slot_stride_for(mode, kblocks);
 }
 __host__ __device__ constexpr int groups_for(int kblocks) { return kblocks <= 1 ? 1 : (kblocks + 1) / 2; }
 
-constexpr size_t kSmemBytes = 1024 /*align slack*/ + kRingBytes + 8 * 32 * 32 * sizeof(float) /*chunk staging*/ +
-                              1024 /*barriers*/;
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+// dynamic shared memory of one CTA: [align slack | ring | chunk staging: 4 KB per epilogue warp | barriers, TMEM slot,
+// shared thresholds]
+__host__ __device__ constexpr size_t smem_bytes_for(int mode) {
+    return 1024 + static_cast<size_t>(ring_bytes_for(mode)) + 4 * epi_sets_for_mode(mode) * 32 * 32 * sizeof(float) + 2048;
+}
+static_assert(smem_bytes_for(RADAR_MODE_DPR) <= 227 * 1024 && smem_bytes_for(RADAR_MODE_KL) <= 227 * 1024 &&
+                  smem_bytes_for(RADAR_MODE_HYBRID) <= 227 * 1024,
+              "shared memory budget");
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -381,14 +427,19 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* stage = reinterpret_cast<float*>(smem + kRingBytes);               // [4 warps][32 columns][32 lanes]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 8 * 32 * 32);
+    float* stage = reinterpret_cast<float*>(smem + ring_bytes_for(MODE));     // [epilogue warps][32 columns][32 lanes]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage + 4 * EPI_SETS * 32 * 32);
     uint64_t* full_bar = bars;                                   // [kMaxSlots][kMaxGroups] (only the leader's are waited on)
     uint64_t* empty_bar = full_bar + kMaxSlots * kMaxGroups;      // [kMaxSlots]
     uint64_t* tfull_bar = empty_bar + kMaxSlots;                  // [ACC_STAGES]
-    uint64_t* tempty_bar = tfull_bar + 3;                         // [ACC_STAGES]  (leader's, 8 arrivals)
-    uint64_t* aready_bar = tempty_bar + 3;                        // [1]           (leader's, 8 arrivals)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aready_bar + 1);
+    uint64_t* tempty_bar = tfull_bar + 8;                         // [ACC_STAGES]  (leader's, 8 arrivals per consuming set)
+    uint64_t* aready_bar = tempty_bar + 8;                        // [1]           (leader's, 8 arrivals)
+    uint64_t* adone_bar = aready_bar + 1;                         // [1] KL: every MMA of an item has completed (both CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(adone_bar + 1);
+    // KL: best threshold of each query row of this CTA over the warp sets, tagged with the item it belongs to:
+    // (item number + 1) << 32 | ord-encoded threshold.  Sets may be one item apart; a tagged word of another item is
+    // ignored by readers and can never overwrite a newer one (atomicMax on the whole word).
+    unsigned long long* thr_sh = reinterpret_cast<unsigned long long*>(tmem_slot + 2);  // [kBlockM]
     const uint32_t ring_addr = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -411,12 +462,14 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
         for (int i = 0; i < kMaxSlots; ++i) mbar_init(&empty_bar[i], 1);
         for (int i = 0; i < ACC_STAGES; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8 * EPI_SETS);
+            mbar_init(&tempty_bar[i], MODE == RADAR_MODE_KL ? 8 * kKlColSplit : 8 * EPI_SETS);  // warps reading one stage
         }
         mbar_init(aready_bar, 8);
+        mbar_init(adone_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_pair(tmem_slot);
+    if (MODE == RADAR_MODE_KL && threadIdx.x >= 64 && threadIdx.x < 64 + kBlockM) thr_sh[threadIdx.x - 64] = 0ull;
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // the peer's barriers are initialised before anything is signalled remotely
@@ -561,7 +614,194 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
                         aph ^= 1;
                     }
                 }
+                if (MODE == RADAR_MODE_KL) {  // sets other than set 0 may still be consuming this item's last tiles
+                    if (elect_one()) umma_commit_pair(adone_bar);
+                    __syncwarp();
+                }
             }
+        }
+    } else if constexpr (MODE == RADAR_MODE_KL) {
+        // ================================ KL epilogue: tile streams x column splits ================================
+        // Tile g (running number over all items of this pair; accumulator stage g mod ACC_STAGES) is filtered by the sets
+        // of stream g mod TS, set (ts, cs) reading columns [cs * COLS, (cs + 1) * COLS) -- 64 columns per
+        // tcgen05.wait::ld.  A stage is handed back when the last of its readers has its columns in registers.
+        constexpr int TS = kKlTileStreams, CS = kKlColSplit;
+        constexpr int COLS = BLOCK_N / CS;
+        static_assert(COLS % 32 == 0 || COLS % 32 == 16, "KL columns per warp must be 32k or 32k + 16");
+        const int quad = warp & 3;
+        const int set = (warp - 2) >> 2;
+        const int ts = set / CS, cs = set % CS;
+        const int col0 = cs * COLS;
+        const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
+        const int r_in_cta = quad * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        float* my_stage = stage + (warp - 2) * 32 * 32 + lane;
+        const int a_cols = a_cols_for(MODE, a.d);
+        uint32_t g = 0;         // running tile number of this pair (the issuer's accumulator stage is g mod ACC_STAGES)
+        uint32_t item_no = 0;
+        for (int64_t item = unit; item < items; item += units, ++item_no) {
+            const int64_t qtile = item % a.q_tiles;
+            const int part = static_cast<int>(item / a.q_tiles);
+            const int64_t qrow = qtile * kTileQ + r_in_tile;
+            const bool valid = qrow < a.q;
+            const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+            const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+            if (set == 0) {
+                // ---- query tile -> TMEM, once every MMA of the previous item has completed ----
+                if (item_no > 0) {
+                    mbar_wait(adone_bar, (item_no - 1) & 1);
+                    tc_fence_after();
+                }
+                const uint4* ksrc = reinterpret_cast<const uint4*>(a.apack + qrow * a_cols);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint4 u0 = __ldg(ksrc + 2 * c), u1 = __ldg(ksrc + 2 * c + 1);
+                    const uint32_t v[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                    tmem_st_x8(tmem_base + lane_addr + A_KL_COL + c * 8, v);
+                }
+                tmem_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(aready_bar);
+            }
+            const float shift = a.qshift[qrow];
+            const uint32_t g0 = (a.parts > 1 || a.gthr_init) ? *reinterpret_cast<volatile const uint32_t*>(a.gthr + qrow) : 0u;
+            uint32_t thr_ord = g0;                                          // ord-encoded canonical-key units, 0 = none
+            float thr = g0 ? ord2f(g0) : -CUDART_INF_F;
+            // inherited thresholds are stepped a few ulps down (see the DPR / hybrid epilogue below for why)
+            auto cmp_of = [&](float t) {
+                const float c = __fadd_rn(t, shift);
+                return c - 4e-7f * (fabsf(c) + fabsf(shift));
+            };
+            float thr_cmp = valid ? (g0 ? cmp_of(thr) : -CUDART_INF_F) : CUDART_INF_F;
+            int cnt = 0;
+            const int64_t slot_idx = (qrow * a.parts + part) * EPI_SETS + set;
+            uint64_t* buf = a.cand + slot_idx * kCandCap;
+            const uint32_t ntiles = static_cast<uint32_t>((row_end - row_begin + tile_step - 1) / tile_step);
+            // first tile of this item that belongs to this set's stream
+            uint32_t j = (static_cast<uint32_t>(ts) + TS - (g % TS)) % TS;
+            for (; j < ntiles; j += TS) {
+                const uint32_t gt = g + j;
+                const uint32_t stg = gt % ACC_STAGES, aph = (gt / ACC_STAGES) & 1u;
+                const int64_t row0 = row_begin + static_cast<int64_t>(j) * tile_step + col0;  // first corpus row of this set's columns
+                if (!a.prepass && EPI_SETS > 1) {
+                    // a compaction of another set may have published a better threshold for this row since
+                    const unsigned long long tw = *reinterpret_cast<volatile unsigned long long*>(thr_sh + r_in_cta);
+                    const uint32_t ts = static_cast<uint32_t>(tw);
+                    if (valid && static_cast<uint32_t>(tw >> 32) == item_no + 1u && ts > thr_ord) {
+                        thr_ord = ts;
+                        thr = ord2f(ts);
+                        thr_cmp = cmp_of(thr);
+                    }
+                }
+                mbar_wait(&tfull_bar[stg], aph);
+                tc_fence_after();
+                const uint32_t t_acc = tmem_base + lane_addr + ACC_COL0 + stg * BLOCK_N + col0;
+                float tmax = -CUDART_INF_F;  // prepass: maximum over the whole tile
+                // one 32-column group of accumulators of this thread's query row, in registers
+                auto filter32 = [&](const float (&cur)[32], const int width, const int64_t rowc) {
+                    if (RADAR_DBG(a.dbg_flags & 5)) {
+                        if (RADAR_DBG(a.dbg_flags & 4)) asm volatile("" ::"f"(cur[0]), "f"(cur[width - 1]));
+                        return;
+                    }
+                    float mm[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) mm[u] = cur[u];
+#pragma unroll
+                    for (int jj = 8; jj < 32; ++jj)
+                        if (jj < width) mm[jj & 7] = fmaxf(mm[jj & 7], cur[jj]);
+                    float m = fmaxf(fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3])), fmaxf(fmaxf(mm[4], mm[5]), fmaxf(mm[6], mm[7])));
+                    if (a.prepass) {
+                        if (rowc + width > row_end) {  // ragged last tile: rows past the end were zero-filled by TMA
+                            m = -CUDART_INF_F;
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj)
+                                if (jj < width && rowc + jj < row_end) m = fmaxf(m, cur[jj]);
+                        }
+                        tmax = fmaxf(tmax, m);
+                        return;
+                    }
+                    if (__any_sync(0xffffffffu, m >= thr_cmp) || RADAR_DBG(a.dbg_scores != nullptr)) {
+                        // rare path.  The eight partial maxima (chain u = columns u, u+8, u+16, u+24) say where the
+                        // survivors are: only chains in which SOME lane has one are staged and compared (a warp-uniform
+                        // branch per chain), typically one or two of the eight.
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (__any_sync(0xffffffffu, mm[u] >= thr_cmp) || RADAR_DBG(a.dbg_scores != nullptr)) {
+#pragma unroll
+                                for (int jj = u; jj < 32; jj += 8) {
+                                    if (jj < width) {
+                                        my_stage[jj * 32] = cur[jj];
+                                        mask |= (cur[jj] >= thr_cmp ? 1u : 0u) << jj;
+                                    }
+                                }
+                            }
+                        }
+                        if (RADAR_DBG(a.dbg_scores != nullptr) && valid) {
+                            for (int jj = 0; jj < width; ++jj)
+                                if (rowc + jj < a.n) a.dbg_scores[qrow * a.n + rowc + jj] = my_stage[jj * 32] - shift;
+                        }
+                        while (mask) {
+                            const int jj = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int64_t row = rowc + jj;
+                            if (row < row_end)
+                                buf[cnt++] = make_composite(__fsub_rn(my_stage[jj * 32], shift), static_cast<uint32_t>(row));
+                        }
+                        __syncwarp();
+                        unsigned need = __ballot_sync(0xffffffffu, cnt > kCandSoft);
+                        while (need) {
+                            const int src_lane = __ffs(need) - 1;
+                            need &= need - 1;
+                            uint64_t* b = reinterpret_cast<uint64_t*>(
+                                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src_lane));
+                            const int n_src = __shfl_sync(0xffffffffu, cnt, src_lane);
+                            const float t = warp_compact(b, n_src, a.kp, lane);
+                            if (lane == src_lane) {
+                                thr = t;
+                                thr_ord = f2ord(t);
+                                thr_cmp = __fadd_rn(t, shift);  // own threshold: exact (every kept key was fl(acc - shift))
+                                cnt = a.kp;
+                                if (EPI_SETS > 1)
+                                    atomicMax(thr_sh + r_in_cta,
+                                              (static_cast<unsigned long long>(item_no + 1u) << 32) | thr_ord);
+                            }
+                        }
+                    }
+                };
+                // 64 columns per tcgen05.wait::ld: a wait after every single load caps TMEM reads at ~128 B/cycle/SM,
+                // two loads per wait and three or four warps per lane quadrant reach ~470 (tools/micro/ldtm_bw.cu)
+#pragma unroll
+                for (int c0 = 0; c0 < COLS; c0 += 64) {
+                    const int w0 = COLS - c0 >= 32 ? 32 : COLS - c0;
+                    const int w1 = COLS - c0 - 32 >= 32 ? 32 : (COLS - c0 - 32 > 0 ? COLS - c0 - 32 : 0);
+                    float v0[32], v1[32];
+                    if (w0 == 32) tmem_ld_x32(t_acc + c0, v0);
+                    else tmem_ld_x16(t_acc + c0, v0);
+                    if (w1 == 32) tmem_ld_x32(t_acc + c0 + 32, v1);
+                    else if (w1 == 16) tmem_ld_x16(t_acc + c0 + 32, v1);
+                    tmem_wait_ld();
+                    if (c0 + 64 >= COLS) {  // this warp's columns are in registers (or already filtered): done with the stage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tempty_bar[stg]);
+                    }
+                    filter32(v0, w0, row0 + c0);
+                    if (w1 > 0) filter32(v1, w1, row0 + c0 + 32);
+                }
+                if (a.prepass && !RADAR_DBG(a.dbg_flags & 5)) {
+                    // every tile is its own contribution to its group's maximum (the sets see different tiles of a group)
+                    if (valid && tmax > -CUDART_INF_F)
+                        atomicMax(a.groupmax + qrow * a.groups + part * a.groups_per_slab + static_cast<int>(j) / a.group_tiles,
+                                  f2ord(__fsub_rn(tmax, shift)));
+                }
+            }
+            g += ntiles;
+            if (a.prepass) continue;
+            a.cnt[slot_idx] = valid ? static_cast<uint32_t>(cnt) : 0u;
+            a.thr[slot_idx] = thr;
+            if (a.parts > 1 && valid && thr > -CUDART_INF_F) atomicMax(a.gthr + qrow, f2ord(thr));
         }
     } else {
         // ================================ epilogue warps (2..5, and 6..9 with two sets) ================================
@@ -829,7 +1069,7 @@ static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cuda
         if (rc) return rc;
     }
     RADAR_CUDA_CHECK(cudaFuncSetAttribute(tc_filter_kernel<MODE, KB_T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kSmemBytes)));
+                                          static_cast<int>(smem_bytes_for(MODE))));
     const int64_t items = fl.q_tiles * fl.parts;
     int64_t units = fl.units;
     if (units < 1) units = 1;
@@ -837,7 +1077,7 @@ static int launch_filter_mode(const FilterLaunch& fl, const FilterArgs& fa, cuda
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
     cfg.blockDim = dim3(threads_for_mode(MODE));
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes_for(MODE);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
