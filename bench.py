@@ -73,6 +73,9 @@ def parse_args():
     ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
                     help="default: fp32 (certified) unless the workload names bf16")
     ap.add_argument("--algo", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--kl-variant", default="auto", choices=["auto", "bf16x3", "f16x1", "f16x2"],
+                    help="filter arithmetic of the KL-only tensor-core paths")
+    ap.add_argument("--overfetch", type=int, default=0, help="candidates kept per query by the filters (0 = automatic)")
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--n", type=int, default=0, help="override total corpus rows")
     ap.add_argument("--q", type=int, default=0, help="override queries per step")
@@ -345,7 +348,8 @@ class Bench:
         if have is not None and (not need_emb or have.emb_f32 is not None) and (not need_probs or have.logq16 is not None):
             return have
         lo, hi = shard_bounds(n_total, self.world, self.rank)
-        index = RadarIndex(D, device=self.dev, idx_offset=lo, precision="fp32", algo=self.args.algo)
+        index = RadarIndex(D, device=self.dev, idx_offset=lo, precision="fp32", algo=self.args.algo,
+                           kl_variant=self.args.kl_variant, overfetch=self.args.overfetch)
         index.reserve(hi - lo, embeddings=need_emb, observations=need_probs)
         g = torch.Generator(device=self.dev).manual_seed(4242)
         centers = u = None

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RADAR_ABI_VERSION 3
+#define RADAR_ABI_VERSION 4
 
 #define RADAR_NUM_OBS 14 /* CheXpert-14, train_expert_models.py:50-65 */
 #define RADAR_OBS_PAD 16 /* K=16 padded contraction */
@@ -71,6 +71,13 @@ enum radar_algo {
     RADAR_ALGO_KL_STREAM = 3   /* KL, <= 256 queries, >= 65 536 cases: tcgen05 stream with pooled candidates (HBM-bound) */
 };
 
+enum radar_kl_variant {
+    RADAR_KL_AUTO = 0,
+    RADAR_KL_BF16X3 = 1, /* bf16 hi/lo split of both operands, three products, table klpack (64 B per case) */
+    RADAR_KL_F16X1 = 2,  /* fp16, one product, table kl16 (32 B per case) */
+    RADAR_KL_F16X2 = 3   /* fp16, query split hi/lo (two products), table kl16 */
+};
+
 /* Corpus shard resident in HBM.  Pointers a mode does not need may be NULL.
  * Built once per index by radar_pack_embeddings / radar_kl_prepare_corpus
  * (replaces faiss.IndexFlatIP.add, modeling_dense_passage_retrieval.py:298). */
@@ -88,6 +95,8 @@ typedef struct radar_corpus {
     float logq_col_max[RADAR_OBS_PAD]; /* per observation j: max_n |logq16[n][j]| (host values); all zero => logq_max_abs
                                           is used for every column.  Only tightens the filter's error bound (fewer exact
                                           re-runs in FP32 mode, tighter initial thresholds on the KL stream path). */
+    const uint16_t* kl16;     /* [n,16]  fp16 RN of 2048 * logq16 (32 B per case): the table the KL-only tensor-core paths
+                                 stream (radar_kl_prepare_corpus); NULL => they use klpack */
 } radar_corpus_t;
 
 /* Query batch.  Pointers a mode does not need may be NULL. */
@@ -114,7 +123,7 @@ typedef struct radar_search_params {
     float alpha;       /* hybrid weight (RetrievalConfig.hybrid_alpha, dpr.py:187); ignored unless HYBRID */
     int32_t overfetch; /* candidates re-scored per query on the filter path; 0 = automatic */
     int32_t num_sms;   /* 0 = all SMs of the device (tests use small values to force multi-part merges) */
-    int32_t reserved;  /* must be 0 */
+    int32_t kl_variant; /* enum radar_kl_variant: filter arithmetic of the KL-only tensor-core paths; 0 = automatic */
 } radar_search_params_t;
 
 /* Per-call statistics written to HOST memory when the pointer is non-NULL (forces a stream sync). */
@@ -155,10 +164,10 @@ int radar_profile_kernel_ms(float* ms_out);
 int radar_pack_embeddings(const float* emb_f32, int64_t n, int d, uint16_t* emb_bf16, float* max_norm,
                           void* stream);
 
-/* probabilities [n,n_obs] (n_obs <= 16, normally 14) -> logq16 [n,16]; klpack [n,32] may be NULL.
+/* probabilities [n,n_obs] (n_obs <= 16, normally 14) -> logq16 [n,16]; klpack [n,32] and kl16 [n,16] may be NULL.
  * q <- clamp(q, eps, 1); if normalize, rows are divided by their fp32 left-to-right sum first. */
 int radar_kl_prepare_corpus(const float* probs, int64_t n, int n_obs, float eps, int normalize,
-                            float* logq16, uint16_t* klpack, void* stream);
+                            float* logq16, uint16_t* klpack, uint16_t* kl16, void* stream);
 
 /* ---- query preparation (K1/K3 query side) ------------------------------------------------------- */
 

@@ -24,11 +24,13 @@ MODE_DPR, MODE_KL, MODE_HYBRID = 0, 1, 2
 PREC_BF16, PREC_FP32 = 0, 1
 ALGO_AUTO, ALGO_SIMT_EXACT, ALGO_TC_FILTER, ALGO_KL_STREAM = 0, 1, 2, 3
 NUM_OBS, OBS_PAD, KLPACK, MAX_K = 14, 16, 32, 128
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MODE_BY_NAME = {"dpr": MODE_DPR, "kl": MODE_KL, "hybrid": MODE_HYBRID}
 PREC_BY_NAME = {"bf16": PREC_BF16, "fp32": PREC_FP32}
 ALGO_BY_NAME = {"auto": ALGO_AUTO, "simt": ALGO_SIMT_EXACT, "tc": ALGO_TC_FILTER, "kl_stream": ALGO_KL_STREAM}
+# filter arithmetic of the KL-only tensor-core paths (enum radar_kl_variant)
+KL_VARIANT_BY_NAME = {"auto": 0, "bf16x3": 1, "f16x1": 2, "f16x2": 3}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
@@ -41,7 +43,7 @@ class CorpusStruct(C.Structure):
         ("n", C.c_int64), ("d", C.c_int32), ("reserved0", C.c_int32),
         ("emb_f32", C.c_void_p), ("emb_bf16", C.c_void_p), ("logq16", C.c_void_p), ("klpack", C.c_void_p),
         ("emb_max_norm", C.c_float), ("logq_max_abs", C.c_float), ("idx_offset", C.c_int64),
-        ("logq_col_max", C.c_float * 16),
+        ("logq_col_max", C.c_float * 16), ("kl16", C.c_void_p),
     ]
 
 
@@ -53,7 +55,7 @@ class QueriesStruct(C.Structure):
 class SearchParams(C.Structure):
     _fields_ = [
         ("mode", C.c_int32), ("precision", C.c_int32), ("algo", C.c_int32), ("k", C.c_int32),
-        ("alpha", C.c_float), ("overfetch", C.c_int32), ("num_sms", C.c_int32), ("reserved", C.c_int32),
+        ("alpha", C.c_float), ("overfetch", C.c_int32), ("num_sms", C.c_int32), ("kl_variant", C.c_int32),
     ]
 
 
@@ -123,7 +125,7 @@ def _declare(l, debug: bool):
                                C.c_void_p]
     l.radar_pack_embeddings.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     l.radar_kl_prepare_corpus.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int, C.c_void_p,
-                                          C.c_void_p, C.c_void_p]
+                                          C.c_void_p, C.c_void_p, C.c_void_p]
     l.radar_kl_prepare_queries.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
     l.radar_merge_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

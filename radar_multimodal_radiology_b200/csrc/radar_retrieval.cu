@@ -10,6 +10,7 @@
 #include "prep_kernels.cuh"
 #include "scan_kernels.cuh"
 #include "tc_filter.cuh"
+#include "kl_filter.cuh"
 #include "kl_stream.cuh"
 
 namespace radar {
@@ -67,6 +68,8 @@ struct Plan {
     size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
     size_t off_groupmax;  // KL threshold prepass
     int groups, group_tiles, tile_stride, groups_per_slab;
+    int klf;           // KL mode: the dedicated many-queries kernel (kl_filter.cuh) runs the main pass
+    int kl_fmt;        // its filter arithmetic (klf::kFmt*); also the KL stream path's table choice
     size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
     // KL stream path
     int n_pad, pool_cap, sample_tiles;
@@ -93,13 +96,40 @@ static int auto_overfetch_kl(int k) {
     return kp;
 }
 
+// KL keys of the fp16 filters carry a 4-7x larger error bound than the bf16 hi/lo split (kl_filter.cuh): the certificate
+// "k'-th filter key + qerr < k-th canonical key" needs a wider gap between rank k and rank k', i.e. more candidates
+static int auto_overfetch_kl_fmt(int k, int fmt) {
+    if (fmt == klf::kFmtBf16x3) return auto_overfetch_kl(k);
+    int kp = fmt == klf::kFmtF16x2 ? (3 * k / 2 + 8 + 7) / 8 * 8 : (2 * k + 12 + 7) / 8 * 8;
+    if (kp < 24) kp = 24;
+    if (kp > kCandSoft) kp = kCandSoft;
+    return kp;
+}
+
 static bool tc_supported(const radar_corpus_t* c, int mode, const DeviceInfo& di) {
     if (di.major != 10) return false;
     if (mode != RADAR_MODE_KL) {
         if (!c->emb_bf16 || c->d % 64 != 0 || c->d > 512 || c->d <= 0) return false;
     }
-    if (mode != RADAR_MODE_DPR && !c->klpack) return false;
+    if (mode == RADAR_MODE_HYBRID && !c->klpack) return false;
+    if (mode == RADAR_MODE_KL && !c->klpack && !c->kl16) return false;
     return c->n >= 1;
+}
+
+// filter arithmetic of the KL-only tensor-core paths: what the caller asked for, else what the corpus carries
+static int resolve_kl_fmt(const radar_corpus_t* c, const radar_search_params_t* p, int* fmt) {
+    switch (p->kl_variant) {
+        case RADAR_KL_AUTO: *fmt = c->kl16 ? klf::kFmtF16x2 : klf::kFmtBf16x3; break;
+        case RADAR_KL_BF16X3: *fmt = klf::kFmtBf16x3; break;
+        case RADAR_KL_F16X1: *fmt = klf::kFmtF16x1; break;
+        case RADAR_KL_F16X2: *fmt = klf::kFmtF16x2; break;
+        default: set_error("bad kl_variant %d", p->kl_variant); return RADAR_E_ARG;
+    }
+    if (*fmt == klf::kFmtBf16x3 ? !c->klpack : !c->kl16) {
+        set_error("kl_variant %d needs corpus.%s", p->kl_variant, *fmt == klf::kFmtBf16x3 ? "klpack" : "kl16");
+        return RADAR_E_ARG;
+    }
+    return RADAR_OK;
 }
 
 static void plan_parts(int64_t q_tiles, int64_t n, int tile_rows, int sms, int waves, int* parts,
@@ -153,7 +183,7 @@ static bool kl_stream_supported(const radar_corpus_t* c, int64_t q, int mode, co
 }
 
 static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_params_t* p, const DeviceInfo& di,
-                     Plan* pl, bool search_after = false) {
+                     Plan* pl, bool search_after = false, bool legacy_kl = false) {
     memset(pl, 0, sizeof *pl);
     const int sms = p->num_sms > 0 ? p->num_sms : di.sms;
     int algo = p->algo;
@@ -224,8 +254,20 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->q_tiles = ceil_div64(q, kScanTQ);
         plan_parts(pl->q_tiles, c->n, kScanTC, sms, 2, &pl->parts, &pl->rows_per_part);
     } else {
-        pl->kp = p->overfetch > 0 ? p->overfetch
-                                  : (p->mode == RADAR_MODE_KL ? auto_overfetch_kl(p->k) : auto_overfetch(p->k));
+        if (p->mode == RADAR_MODE_KL && !legacy_kl) {
+            int rc = resolve_kl_fmt(c, p, &pl->kl_fmt);
+            if (rc) return rc;
+            pl->klf = 1;
+            pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl_fmt(p->k, pl->kl_fmt);
+        } else if (p->mode == RADAR_MODE_KL) {  // debug key dump: the KL mode of the general filter (bf16 hi/lo, klpack)
+            if (!c->klpack) {
+                set_error("the KL key dump needs corpus.klpack");
+                return RADAR_E_ARG;
+            }
+            pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl(p->k);
+        } else {
+            pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch(p->k);
+        }
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
@@ -235,10 +277,11 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         if (units < 1) units = 1;
         if (units > tc::kMaxUnits) units = tc::kMaxUnits;
         pl->units = units;
-        plan_parts_filter(pl->q_tiles, c->n, tc::block_n_for_mode(p->mode), units, &pl->parts, &pl->rows_per_part);
+        plan_parts_filter(pl->q_tiles, c->n, pl->klf ? klf::kBlockN : tc::block_n_for_mode(p->mode), units, &pl->parts,
+                          &pl->rows_per_part);
     }
     const int64_t q_pad = pl->q_tiles * pl->tile_q;
-    pl->buf_parts = pl->parts * (algo == RADAR_ALGO_TC_FILTER ? tc::epi_sets_for_mode(p->mode) : 1);
+    pl->buf_parts = pl->parts * (algo == RADAR_ALGO_TC_FILTER ? (pl->klf ? klf::kE : tc::epi_sets_for_mode(p->mode)) : 1);
     pl->off_cand = carve(sizeof(uint64_t) * q_pad * pl->buf_parts * kCandCap);
     pl->off_cnt = carve(sizeof(uint32_t) * q_pad * pl->buf_parts);
     pl->off_thr = carve(sizeof(float) * q_pad * pl->buf_parts);
@@ -251,22 +294,22 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
     if (algo == RADAR_ALGO_TC_FILTER) {
         pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
         // KL with many queries over a small corpus: the cold-start survivors (~k' ln n per query) cost more than a second
-        // sweep of the (cheap) KL contraction, so a prepass collects group maxima and the real pass starts from
-        // near-exact thresholds.  Groups: about 384 per query, at least 4 k'.
-        if (p->mode == RADAR_MODE_KL && c->n <= (2ll << 20) && pl->q_tiles >= 8) {
-            const int64_t c_tiles = ceil_div64(c->n, tc::block_n_for_mode(RADAR_MODE_KL));
-#ifndef RADAR_KL_PREPASS_TILES
-#define RADAR_KL_PREPASS_TILES 768
+        // (partial) sweep of the cheap KL contraction, so a prepass over every tile_stride-th tile collects group maxima
+        // and the real pass starts from near-exact thresholds (kl_filter.cuh).  About 512 groups per query.
+        if (pl->klf && c->n <= (2ll << 20) && pl->q_tiles >= 8 && pl->kp <= klf::kMaxKpPrepass) {
+#ifndef RADAR_KLF_PREPASS_STRIDE
+#define RADAR_KLF_PREPASS_STRIDE 2
 #endif
-            int64_t stride = c_tiles / RADAR_KL_PREPASS_TILES;  // the prepass visits about that many sampled tiles (up to 2x)
-            if (stride < 1) stride = 1;
-            // groups are formed per slab (a slab's sampled tiles are numbered from the slab start), so bound them per slab
-            const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, tc::block_n_for_mode(RADAR_MODE_KL)), stride);
-            int64_t gt = ceil_div64(slab_tiles * pl->parts, 384);
-            if (gt < 1) gt = 1;
-            const int64_t groups_per_slab = ceil_div64(slab_tiles, gt);
+            const int64_t stride = RADAR_KLF_PREPASS_STRIDE;
+            const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, klf::kBlockN), stride);
+            int64_t tgs = 512 / (static_cast<int64_t>(pl->parts) * klf::kE);
+            if (tgs > slab_tiles) tgs = slab_tiles;
+            if (tgs < 1) tgs = 1;
+            const int64_t gt = ceil_div64(slab_tiles, tgs);
+            tgs = ceil_div64(slab_tiles, gt);
+            const int64_t groups_per_slab = tgs * klf::kE;
             const int64_t groups = groups_per_slab * pl->parts;
-            if (groups >= 4 * pl->kp && groups <= 32 * tc::kMaxGroups32) {
+            if (groups >= 4 * pl->kp && groups <= klf::kMaxGroupsK) {
                 pl->groups = static_cast<int>(groups);
                 pl->group_tiles = static_cast<int>(gt);
                 pl->tile_stride = static_cast<int>(stride);
@@ -425,13 +468,13 @@ int radar_pack_embeddings(const float* emb_f32, int64_t n, int d, uint16_t* emb_
 }
 
 int radar_kl_prepare_corpus(const float* probs, int64_t n, int n_obs, float eps, int normalize, float* logq16,
-                            uint16_t* klpack, void* stream) {
+                            uint16_t* klpack, uint16_t* kl16, void* stream) {
     RADAR_ARG_CHECK(probs && logq16 && n >= 0, "kl_prepare_corpus: null pointer");
     RADAR_ARG_CHECK(n_obs >= 1 && n_obs <= RADAR_NUM_OBS, "n_obs=%d out of range [1,%d]", n_obs, RADAR_NUM_OBS);
     RADAR_ARG_CHECK(eps > 0.0f && eps < 1.0f, "eps must be in (0,1)");
     if (n == 0) return RADAR_OK;
     kl_prepare_corpus_kernel<<<static_cast<unsigned>(ceil_div64(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        probs, n, n_obs, eps, normalize, logq16, reinterpret_cast<__nv_bfloat16*>(klpack));
+        probs, n, n_obs, eps, normalize, logq16, reinterpret_cast<__nv_bfloat16*>(klpack), reinterpret_cast<__half*>(kl16));
     RADAR_CUDA_CHECK(cudaGetLastError());
     return RADAR_OK;
 }
@@ -454,7 +497,15 @@ size_t radar_search_workspace_bytes(const radar_corpus_t* corpus, int64_t q, con
     if (get_device_info(&di)) return 0;
     Plan pl;
     if (make_plan(corpus, q, params, di, &pl)) return 0;
-    return pl.total + 256;
+    size_t total = pl.total;
+#ifdef RADAR_DEBUG
+    // the key dump of KL mode runs the general filter, whose plan differs from the dedicated KL kernel's
+    if (params->mode == RADAR_MODE_KL && corpus->klpack && pl.algo == RADAR_ALGO_TC_FILTER) {
+        Plan legacy;
+        if (make_plan(corpus, q, params, di, &legacy, false, true) == RADAR_OK && legacy.total > total) total = legacy.total;
+    }
+#endif
+    return total + 256;
 }
 
 int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, const radar_search_params_t* params,
@@ -620,9 +671,22 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         fl.groupmax = pl.groups ? reinterpret_cast<uint32_t*>(ws + pl.off_groupmax) : nullptr;
         fl.ev_start = g_prof_start; fl.ev_stop = g_prof_stop;
         int nl = 0;
-        rc = tc::launch_filter(fl, st, &nl);
-        if (rc) return rc;
-        clk_dev = fl.clk_dev;
+        if (pl.klf) {
+            klf::KlfLaunch kl{};
+            kl.corpus = corpus; kl.queries = queries; kl.fmt = pl.kl_fmt; kl.q = q; kl.q_tiles = pl.q_tiles;
+            kl.parts = pl.parts; kl.rows_per_part = pl.rows_per_part; kl.kp = pl.kp; kl.cand = cand; kl.cnt = cnt;
+            kl.thr = thr; kl.gthr = fl.gthr; kl.qerr = qerr; kl.apack = fl.apack; kl.units = pl.units;
+            kl.groupmax = fl.groupmax; kl.groups = pl.groups; kl.group_tiles = pl.group_tiles;
+            kl.tile_stride = pl.tile_stride; kl.groups_per_slab = pl.groups_per_slab;
+            kl.ev_start = g_prof_start; kl.ev_stop = g_prof_stop;
+            rc = klf::launch_kl_filter(kl, st, &nl);
+            if (rc) return rc;
+            clk_dev = kl.clk_dev;
+        } else {
+            rc = tc::launch_filter(fl, st, &nl);
+            if (rc) return rc;
+            clk_dev = fl.clk_dev;
+        }
         launches += nl;
         select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
             cand, cnt, thr, q, nullptr, pl.buf_parts, kCandCap, pl.R, sel, bound);
@@ -694,7 +758,7 @@ int radar_debug_filter_keys(const radar_corpus_t* corpus, const radar_queries_t*
     radar_search_params_t p2 = *params;
     p2.algo = RADAR_ALGO_TC_FILTER;
     Plan pl;
-    rc = make_plan(corpus, q, &p2, di, &pl);
+    rc = make_plan(corpus, q, &p2, di, &pl, false, true);
     if (rc) return rc;
     if (!workspace || workspace_bytes < pl.total) {
         set_error("workspace too small: need %zu bytes, got %zu", pl.total, workspace_bytes);

@@ -120,6 +120,9 @@ class _RowStore:
         return st
 
 
+_TABLES = ("emb_f32", "emb_bf16", "logq16", "klpack", "kl16")  # resident corpus tensors (all optional)
+
+
 class RadarIndex:
     """Exact flat index over (embedding, observation-probability) rows resident in HBM.
 
@@ -129,7 +132,7 @@ class RadarIndex:
 
     def __init__(self, d: int = 512, device: Union[str, torch.device] = "cuda", precision: str = "bf16",
                  eps: float = 1e-8, normalize: bool = False, idx_offset: int = 0, algo: str = "auto",
-                 overfetch: int = 0, num_sms: int = 0, keep_bf16: bool = True):
+                 overfetch: int = 0, num_sms: int = 0, keep_bf16: bool = True, kl_variant: str = "auto"):
         self.d = int(d)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -143,6 +146,9 @@ class RadarIndex:
         self.idx_offset = int(idx_offset)
         self.overfetch, self.num_sms = int(overfetch), int(num_sms)
         self.keep_bf16 = keep_bf16
+        if kl_variant not in L.KL_VARIANT_BY_NAME:
+            raise ValueError(f"kl_variant must be one of {sorted(L.KL_VARIANT_BY_NAME)}")
+        self.kl_variant = kl_variant
         self._stores = {}  # name -> _RowStore (emb_f32, emb_bf16, logq16, klpack)
         self.emb_max_norm = 0.0
         self.logq_col_max = [0.0] * L.OBS_PAD  # per observation: max |log q| over the rows added so far
@@ -169,6 +175,7 @@ class RadarIndex:
     emb_bf16 = property(lambda self: self._view("emb_bf16"), lambda self, t: self._set("emb_bf16", t))
     logq16 = property(lambda self: self._view("logq16"), lambda self, t: self._set("logq16", t))
     klpack = property(lambda self: self._view("klpack"), lambda self, t: self._set("klpack", t))
+    kl16 = property(lambda self: self._view("kl16"), lambda self, t: self._set("kl16", t))
 
     def _store(self, name: str, cols: int, dtype: torch.dtype) -> _RowStore:
         st = self._stores.get(name)
@@ -185,6 +192,7 @@ class RadarIndex:
         if observations:
             self._store("logq16", L.OBS_PAD, torch.float32).reserve(rows)
             self._store("klpack", L.KLPACK, torch.bfloat16).reserve(rows)
+            self._store("kl16", L.OBS_PAD, torch.float16).reserve(rows)
         self.generation += 1
 
     # ---- faiss.IndexFlatIP surface ------------------------------------------------------------------
@@ -230,9 +238,11 @@ class RadarIndex:
             return
         logq = self._store("logq16", L.OBS_PAD, torch.float32).append_slot(n)
         pack = self._store("klpack", L.KLPACK, torch.bfloat16).append_slot(n)
+        kl16 = self._store("kl16", L.OBS_PAD, torch.float16).append_slot(n)
         with L.device_guard(self.device):
             L.check(L.lib().radar_kl_prepare_corpus(L.ptr(p), n, L.NUM_OBS, self.eps, int(self.normalize),
-                                                    L.ptr(logq), L.ptr(pack), L.current_stream_ptr(self.device)),
+                                                    L.ptr(logq), L.ptr(pack), L.ptr(kl16),
+                                                    L.current_stream_ptr(self.device)),
                     "radar_kl_prepare_corpus")
         col = logq.abs().amax(dim=0).tolist()  # one sync per add; tightens the filter's error bound
         self.logq_col_max = [max(a, float(b)) for a, b in zip(self.logq_col_max, col)]
@@ -250,11 +260,12 @@ class RadarIndex:
 
         The reference persists model weights with safetensors (train_expert_models.py:279-283) and never persists the
         retrieval index (dpr.py:278-303); here the resident tensors are stored as they sit in HBM -- canonical fp32
-        embeddings, their bf16 copy, the fp32 log table and its bf16 [hi|lo] pack -- so loading is a plain copy."""
+        embeddings, their bf16 copy, the fp32 log table, its bf16 [hi|lo] pack and its fp16 copy -- so loading is a plain
+        copy."""
         import json
         from safetensors.torch import save_file
         tensors = {}
-        for name in ("emb_f32", "emb_bf16", "logq16", "klpack"):
+        for name in _TABLES:
             t = getattr(self, name)
             if t is not None:
                 tensors[name] = t.detach().cpu().contiguous()
@@ -279,7 +290,7 @@ class RadarIndex:
         args.update(kw)
         index = cls(**args)
         tensors = load_file(path + ".safetensors", device=str(index.device))
-        for name in ("emb_f32", "emb_bf16", "logq16", "klpack"):
+        for name in _TABLES:
             if name in tensors:
                 setattr(index, name, tensors[name].contiguous())
         index.emb_max_norm = float(meta["emb_max_norm"])
@@ -296,10 +307,11 @@ class RadarIndex:
             raise ValueError(f"rows [{lo},{hi}) out of range for an index of {self.ntotal} rows")
         args = dict(d=self.d, device=self.device, precision=self.precision, eps=self.eps, normalize=self.normalize,
                     idx_offset=self.idx_offset + lo if idx_offset is None else idx_offset, algo=self.algo,
-                    overfetch=self.overfetch, num_sms=self.num_sms, keep_bf16=self.keep_bf16)
+                    overfetch=self.overfetch, num_sms=self.num_sms, keep_bf16=self.keep_bf16,
+                    kl_variant=self.kl_variant)
         args.update(kw)
         v = RadarIndex(**args)
-        for name in ("emb_f32", "emb_bf16", "logq16", "klpack"):
+        for name in _TABLES:
             t = self._view(name)
             if t is not None:
                 setattr(v, name, t[lo:hi])
@@ -323,6 +335,7 @@ class RadarIndex:
                 raise RuntimeError("embedding rows and observation rows differ in count")
             c.logq16 = L.ptr(self.logq16)
             c.klpack = L.ptr(self.klpack)
+            c.kl16 = L.ptr(self.kl16)
         c.emb_max_norm = self.emb_max_norm
         c.logq_max_abs = abs(math.log(self.eps)) * 1.0001
         c.idx_offset = self.idx_offset
@@ -353,7 +366,8 @@ class RadarIndex:
                mask: Optional[ArrayLike] = None, alpha: float = 0.5, mode: Optional[str] = None,
                precision: Optional[str] = None, algo: Optional[str] = None, collect_stats: bool = False,
                prepared: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               workspace: Optional[Workspace] = None, return_packed: bool = False):
+               workspace: Optional[Workspace] = None, return_packed: bool = False,
+               kl_variant: Optional[str] = None, overfetch: Optional[int] = None):
         """(scores float32[Q,k], ids int64[Q,k]) as CUDA tensors, best first.
 
         DPR: inner products, descending (``IndexFlatIP.search``).  KL: KL(p_query||q_case), ascending.
@@ -362,6 +376,8 @@ class RadarIndex:
         ``k`` may exceed ``RADAR_MAX_K`` (faiss accepts any k, dpr.py:313): the ranking is then paged through in
         exact ``RADAR_MAX_K``-sized calls (``radar_queries.after_*``).  ``return_packed`` additionally returns the
         result as sortable uint64 words (int64 tensor of bit patterns) -- the form row-sharded ranks exchange.
+        ``kl_variant`` / ``overfetch`` override the index-wide settings for this call (filter arithmetic of the KL-only
+        tensor-core paths; candidates kept per query by a filter).
         """
         m = self.resolve_mode(mode, x is not None, query_probs is not None or prepared is not None)
         n = self.ntotal
@@ -397,8 +413,10 @@ class RadarIndex:
             return (out_s, out_i, out_p) if return_packed else (out_s, out_i)
         prec = L.PREC_BY_NAME[precision or self.precision]
         alg = L.ALGO_BY_NAME[algo or self.algo]
+        tune = (L.KL_VARIANT_BY_NAME[kl_variant or self.kl_variant], self.overfetch if overfetch is None else int(overfetch))
         if k <= L.MAX_K:
-            self._search_call(m, xq, p16, ent, k, alpha, prec, alg, out_s, out_i, out_p, None, collect_stats, workspace)
+            self._search_call(m, xq, p16, ent, k, alpha, prec, alg, out_s, out_i, out_p, None, collect_stats, workspace,
+                              tune=tune)
         else:
             # page through the exact ranking, RADAR_MAX_K results at a time, each call continuing strictly after the
             # last (score, id) of the previous one
@@ -420,7 +438,7 @@ class RadarIndex:
         return (out_s, out_i, out_p) if return_packed else (out_s, out_i)
 
     def _search_call(self, m, xq, p16, ent, k, alpha, prec, alg, out_s, out_i, out_p, after, collect_stats,
-                     workspace, library=None) -> None:
+                     workspace, library=None, tune=None) -> None:
         """One ``radar_search`` call (k <= RADAR_MAX_K) on already validated device tensors."""
         qs = L.QueriesStruct()
         qs.q = int((xq if xq is not None else p16).shape[0])
@@ -432,7 +450,8 @@ class RadarIndex:
         sp = L.SearchParams()
         sp.mode, sp.k, sp.alpha = m, k, float(alpha)
         sp.precision, sp.algo = prec, alg
-        sp.overfetch, sp.num_sms = self.overfetch, self.num_sms
+        sp.kl_variant, sp.overfetch = tune if tune is not None else (L.KL_VARIANT_BY_NAME[self.kl_variant], self.overfetch)
+        sp.num_sms = self.num_sms
         lib = library or L.lib()
         with L.device_guard(self.device, lib):
             nbytes = lib.radar_search_workspace_bytes(C.byref(cs), qs.q, C.byref(sp))
@@ -534,7 +553,7 @@ class GraphedSearch:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._workspace.frozen = True
-        self._corpus = tuple(self._base._view(nm) for nm in ("emb_f32", "emb_bf16", "logq16", "klpack"))
+        self._corpus = tuple(self._base._view(nm) for nm in _TABLES)
         self._generation = self._base.generation
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -71,3 +71,50 @@ def test_filter_error_bound_holds_for_every_pair(mode, alpha, variant):
     assert worst <= 1.0, f"bound violated: worst |canonical - filter| / qerr = {worst:.3f}"
     if mode != co.MODE_KL:
         assert worst >= 0.01  # the bound is not vacuous: bf16 rounding of 512-d operands really is of this order
+
+
+def f16(x):
+    return np.ascontiguousarray(x, dtype=np.float32).astype(np.float16).astype(np.float32)
+
+
+def fp16_filter_keys_and_bound(fmt, p16, ent, logq, col_max):
+    """float64 emulation of the KL-only fp16 filters (csrc/kl_filter.cuh: fmt 1 = one product fp16(2^13 v) . fp16(2^11 L),
+    fmt 2 = query split hi/lo, two products) + the fp32 bound of klf_pack_kernel."""
+    v = p16.astype(np.float32)
+    vs = v * np.float32(8192.0)
+    v_hi = f16(vs)
+    v_lo = f16(vs - v_hi)
+    l16 = f16(logq.astype(np.float32) * np.float32(2048.0))
+    assert np.all((l16 == 0) | (np.abs(l16) >= 6.2e-5)) and np.all((v_hi == 0) | (v_hi >= 6.2e-5)), "subnormal operand"
+    d = np.float64
+    acc = v_hi.astype(d) @ l16.astype(d).T
+    if fmt == 2:
+        acc += v_lo.astype(d) @ l16.astype(d).T
+    f = acc / 2.0 ** 24 - ent.astype(d)[:, None]
+    kl_mag = (np.abs(v).astype(d) * (col_max * 1.0001)[None, :]).sum(1)
+    sl = ((v != 0) * (col_max * 1.0001)[None, :]).sum(1)
+    rel = 1.13e-3 if fmt == 1 else 6.3e-4
+    e = rel * kl_mag + 8e-9 * sl + 1e-6 * (np.abs(ent.astype(d)) + kl_mag) + 1e-30
+    return f, e
+
+
+@pytest.mark.parametrize("fmt", [1, 2])
+@pytest.mark.parametrize("variant", ["plain", "clamped", "near_one"])
+def test_fp16_kl_filter_error_bound_holds_for_every_pair(fmt, variant):
+    p = make_problem(1500, 48, seed=62)
+    if variant == "clamped":
+        p["c_pr"][::3, ::2] = 0.0
+        p["c_pr"][1::3, 1::2] = 1.0
+        p["q_pr"][::2, :5] = 1.0
+        p["q_pr"][1::2, 5:9] = 0.0   # clamped to 1e-8: the smallest non-zero query weight
+    if variant == "near_one":  # log q just below zero: the smallest non-zero table entries
+        p["c_pr"][::2, :7] = np.float32(1.0) - np.float32(2.0 ** -24)
+        p["c_pr"][1::2, 7:] = np.float32(1.0) - np.float32(2.0 ** -20)
+    logq = co.prepare_corpus(p["c_pr"])
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"])
+    col_max = np.abs(logq).max(axis=0).astype(np.float64)
+    f, e = fp16_filter_keys_and_bound(fmt, p16, ent, logq, col_max)
+    c = canonical_keys(co.MODE_KL, p, p16, ent, logq, 0.5)
+    worst = (np.abs(c - f) / e[:, None]).max()
+    assert worst <= 1.0, f"bound violated: worst |canonical - filter| / qerr = {worst:.3f}"
+    assert worst >= 0.01

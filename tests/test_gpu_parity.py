@@ -261,6 +261,44 @@ def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
     assert idx.last_stats.uncertified == 0  # no certificate / fallback in bf16 mode
 
 
+@pytest.mark.parametrize("variant", ["bf16x3", "f16x1", "f16x2"])
+@pytest.mark.parametrize("n,q,k", [(30000, 500, 10), (9000, 300, 32), (150000, 2300, 10), (150000, 2300, 5)])
+def test_kl_filter_variants_fp32_certified_and_bf16_recall(dev, variant, n, q, k):
+    """The dedicated many-queries KL kernel (csrc/kl_filter.cuh) in each of its filter arithmetics: bf16 hi/lo x 3 products
+    on klpack, fp16 x 1 and fp16 x 2 products on kl16.  fp32 precision = bit-identical to the oracle (certificate or
+    exact re-run); bf16 precision = recall@k >= 0.999 with canonical scores.  150 000 cases x 2 300 queries runs the
+    group-maximum PREPASS (>= 8 query tiles), the smaller shapes the cold start."""
+    from oracle import c_oracle as co
+    p = make_problem(n, q, d=64, seed=40 + k)
+    idx = _index(p, dev, precision="fp32", algo="tc", kl_variant=variant)
+    s, i = _search(idx, p, "kl", k)
+    ws, wi = _oracle(p, "kl", k)
+    st = idx.last_stats
+    assert st.algo_used == 2
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    assert st.uncertified <= 0.25 * q, f"certificate failed for {st.uncertified}/{q} queries ({variant}, k'={st.kprime})"
+    s, i = _search(idx, p, "kl", k, precision="bf16")
+    recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)])
+    assert recall >= 0.999, recall
+    logq = co.prepare_corpus(p["c_pr"])
+    p16, ent = co.prepare_queries(p["q_pr"], p["mask"])
+    assert np.array_equal(s, co.score_pairs(1, i, p16=p16, entropy=ent, logq16=logq))
+
+
+def test_kl_filter_duplicate_rows_and_ragged_tail(dev):
+    """Ties (duplicated cases) keep the smaller id and the zero-filled tail of the last tile never surfaces, in every
+    filter arithmetic and with the prepass on."""
+    p = make_problem(131077, 2100, d=64, seed=47)
+    p["c_pr"][70000:70040] = p["c_pr"][100:140]      # exact duplicates far apart
+    p["c_pr"][131070:131077] = p["c_pr"][200:207]    # ... and in the ragged tail of the last tile
+    p["q_pr"][:40] = p["c_pr"][100:140]              # queries whose best match is duplicated (KL = 0 twice)
+    ws, wi = _oracle(p, "kl", 10)
+    for variant in ("bf16x3", "f16x1", "f16x2"):
+        idx = _index(p, dev, precision="fp32", algo="tc", kl_variant=variant)
+        s, i = _search(idx, p, "kl", 10)
+        assert np.array_equal(i, wi) and np.array_equal(s, ws), variant
+
+
 # ---------------------------------------------------------------------------------------------------
 # KL stream path (few queries, large corpus: pooled candidates, tcgen05 with cases on the M side)
 # ---------------------------------------------------------------------------------------------------

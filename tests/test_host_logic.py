@@ -31,11 +31,11 @@ def test_abi_library_loads_and_exports_every_declared_symbol(built_lib):
     assert declared_dbg - declared == set(_lib.DEBUG_EXPORTS)
     for name in declared:
         assert hasattr(built_lib, name), f"{name} not exported"
-    assert built_lib.radar_abi_version() == _lib.ABI_VERSION == 3
+    assert built_lib.radar_abi_version() == _lib.ABI_VERSION == 4
     assert _exported(_lib.LIB_PATH) == declared            # nothing undeclared leaks out of the release library
     assert _exported(_lib.DBG_LIB_PATH) == declared_dbg
     dbg = _lib.debug_lib()
-    assert dbg.radar_abi_version() == 3 and hasattr(dbg, "radar_debug_filter_keys")
+    assert dbg.radar_abi_version() == 4 and hasattr(dbg, "radar_debug_filter_keys")
 
 
 def test_release_library_reads_no_environment_variables():
