@@ -39,18 +39,37 @@ namespace klf {
 
 using namespace tc;  // PTX wrappers, descriptors, cluster helpers
 
-#ifndef RADAR_KLF_E
-#define RADAR_KLF_E 4
+#ifndef RADAR_KLF_PAIR
+#define RADAR_KLF_PAIR 1
 #endif
-constexpr int kE = RADAR_KLF_E;            // epilogue warps per TMEM lane quadrant == 64-column slices of a tile
-constexpr int kBlockN = 64 * kE;           // corpus rows per tile (whole pair)
-constexpr int kStages = 512 / kBlockN;     // accumulator stages
+#ifndef RADAR_KLF_CS
+#define RADAR_KLF_CS 4
+#endif
+#ifndef RADAR_KLF_TS
+#define RADAR_KLF_TS 1
+#endif
+#ifndef RADAR_KLF_ONE_THREAD
+#define RADAR_KLF_ONE_THREAD 0
+#endif
+// producer / issuer loops run by ONE thread (no per-tile elect + reconvergence) or by the whole warp with an elected lane
+constexpr bool kOneThread = RADAR_KLF_ONE_THREAD != 0;
+constexpr bool kPair = RADAR_KLF_PAIR != 0;  // CTA pairs (tcgen05 cta_group::2, M = 256) or single CTAs (M = 128, all hand-offs CTA-local)
+constexpr int kCtas = kPair ? 2 : 1;
+constexpr int kTileQK = kBlockM * kCtas;   // query rows per work tile
+constexpr int kCS = RADAR_KLF_CS;          // warps per lane quadrant that split the columns of one tile (64 columns each)
+constexpr int kTS = RADAR_KLF_TS;          // tile streams: tile g of a pair is filtered by the warps of stream g mod kTS
+constexpr int kE = kCS * kTS;              // epilogue warps per TMEM lane quadrant == candidate buffers per (query, slab)
+constexpr int kBlockN = 64 * kCS;          // corpus rows per tile (whole pair / CTA)
+constexpr int kStages = 512 / kBlockN > 8 ? 8 : 512 / kBlockN;  // accumulator stages
 constexpr int kThreadsK = 64 + 128 * kE;   // warp 0 TMA, warp 1 MMA + TMEM alloc, 4 E epilogue warps
+// a stream waits for "its" tile on an mbarrier PARITY, which is only sound when the previous phase of that barrier is
+// known to be complete: with kStages % kTS == 0 the previous user of a stage is the same stream
+static_assert(kStages % kTS == 0, "tile streams must divide the accumulator stages");
 constexpr int kSlotsK = 8;                 // corpus tile ring
 constexpr int kASlotBytes = kBlockM * 64;  // one CTA's half of a query tile: 128 rows x [hi(16) | lo(16)] halves
 constexpr int kMaxKpPrepass = 48;          // the threshold kernel keeps k' values per query in shared memory
 constexpr int kMaxGroupsK = 1024;
-static_assert(kE >= 2 && kE <= 4 && kBlockN <= 256 && kBlockN % 16 == 0 && kStages >= 2, "KL filter geometry");
+static_assert(kE >= 1 && kE <= 4 && kBlockN <= 256 && kBlockN % 16 == 0 && kStages >= 2, "KL filter geometry");
 
 constexpr int kFmtBf16x3 = 0, kFmtF16x1 = 1, kFmtF16x2 = 2;
 constexpr float kScaleV = 8192.0f, kScaleL = 2048.0f;        // 2^13, 2^11
@@ -58,7 +77,7 @@ constexpr float kAccScale = 16777216.0f;                     // 2^24 = kScaleV *
 constexpr float kAccInv = 1.0f / 16777216.0f;
 
 __host__ __device__ constexpr int row_bytes(int fmt) { return fmt == kFmtBf16x3 ? 64 : 32; }
-__host__ __device__ constexpr int slot_bytes(int fmt) { return (kBlockN / 2) * row_bytes(fmt); }
+__host__ __device__ constexpr int slot_bytes(int fmt) { return (kBlockN / kCtas) * row_bytes(fmt); }  // per CTA
 __host__ __device__ constexpr size_t smem_bytes(int fmt) {
     return 1024 + static_cast<size_t>(kSlotsK) * slot_bytes(fmt) + 2 * kASlotBytes + 4 * kE * 32 * 32 * sizeof(float) + 1024;
 }
@@ -79,19 +98,61 @@ __device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint6
         : "memory");
 }
 
+// single-CTA flavours of the pair helpers in tc_filter.cuh
+__device__ __forceinline__ void umma_ss1(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit1(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_1(const CUtensorMap* map, uint32_t bar_addr, uint32_t dst_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_addr),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc1(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc1(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kTmemCols) : "memory");
+}
+// the flavour this build uses
+__device__ __forceinline__ void klf_mma(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+    if constexpr (kPair) umma_ss2(d, a, b, idesc, acc);
+    else umma_ss1(d, a, b, idesc, acc);
+}
+__device__ __forceinline__ void klf_commit(uint64_t* bar) {
+    if constexpr (kPair) umma_commit_pair(bar);
+    else umma_commit1(bar);
+}
+__device__ __forceinline__ void klf_tma(const CUtensorMap* map, uint32_t bar_addr, uint32_t dst, int c0, int c1) {
+    if constexpr (kPair) tma_load_2d_pair(map, bar_addr, dst, c0, c1);
+    else tma_load_2d_1(map, bar_addr, dst, c0, c1);
+}
+
 // barrier helpers on precomputed 32-bit shared addresses (the epilogue loop must not re-derive them every tile)
+__device__ __forceinline__ bool mbar_try_a(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     uint32_t spins = 0;
-    while (true) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (ok) break;
+    while (!mbar_try_a(addr, parity)) {
         if (++spins > kSpinLimit) {
             printf("radar kl_filter: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
@@ -177,9 +238,9 @@ struct KlfArgs {
 template <int FMT, bool PREPASS>
 __global__ void __launch_bounds__(kThreadsK, 1)
 klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_c, const KlfArgs a) {
-    constexpr int LOAD_N = kBlockN / 2;
+    constexpr int LOAD_N = kBlockN / kCtas;
     constexpr int SLOT = slot_bytes(FMT);
-    constexpr uint32_t IDESC = FMT == kFmtBf16x3 ? make_idesc_mn(kTileQ, kBlockN) : make_idesc_f16_mn(kTileQ, kBlockN);
+    constexpr uint32_t IDESC = FMT == kFmtBf16x3 ? make_idesc_mn(kTileQK, kBlockN) : make_idesc_f16_mn(kTileQK, kBlockN);
     constexpr float SCALE = FMT == kFmtBf16x3 ? 1.0f : kAccScale;
     constexpr float INV = FMT == kFmtBf16x3 ? 1.0f : kAccInv;
 
@@ -198,9 +259,9 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     const uint32_t ring_addr = smem_u32(smem), abuf_addr = smem_u32(abuf);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t cta_rank = cluster_ctarank();
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
-    const int64_t unit = blockIdx.x >> 1, units = gridDim.x >> 1;
+    const int64_t unit = kPair ? blockIdx.x >> 1 : blockIdx.x, units = kPair ? gridDim.x >> 1 : gridDim.x;
     const int64_t items = a.q_tiles * a.parts;
     const int64_t tile_step = static_cast<int64_t>(kBlockN) * a.tile_stride;
 
@@ -218,7 +279,7 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8 * kE);
+            mbar_init(&tempty_bar[i], 4 * kCS * kCtas);  // warps reading one stage: 4 quadrants x kCS (x 2 CTAs)
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&afull_bar[i], 1);
@@ -226,10 +287,13 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc_pair(tmem_slot);
+    if (warp == 1) {
+        if constexpr (kPair) tmem_alloc_pair(tmem_slot);
+        else tmem_alloc1(tmem_slot);
+    }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();
+    if constexpr (kPair) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (tmem_base != 0) {
@@ -239,67 +303,74 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
     if (warp == 0) {
         // ================================ TMA producer (every CTA: its halves) ================================
-        uint32_t slot = 0, sph = 0, item_no = 0;
-        for (int64_t item = unit; item < items; item += units, ++item_no) {
-            const int64_t qtile = item % a.q_tiles;
-            const int part = static_cast<int>(item / a.q_tiles);
-            const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
-            const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
-            const uint32_t ab = item_no & 1u;
-            if (item_no >= 2) mbar_wait(&afree_bar[ab], ((item_no >> 1) - 1u) & 1u);  // MMAs of item_no - 2 are done
-            if (elect_one()) {
-                if (leader) mbar_expect_tx(&afull_bar[ab], 2 * kASlotBytes);
-                tma_load_2d_pair(&map_q, smem_u32(&afull_bar[ab]), abuf_addr + ab * kASlotBytes, 0,
-                                 static_cast<int>(qtile * kTileQ) + static_cast<int>(cta_rank) * kBlockM);
-            }
-            __syncwarp();
-            for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
-                mbar_wait(&empty_bar[slot], sph ^ 1);
-                if (elect_one()) {
-                    if (leader) mbar_expect_tx(&full_bar[slot], 2 * SLOT);
-                    tma_load_2d_pair(&map_c, smem_u32(&full_bar[slot]), ring_addr + slot * SLOT, 0,
-                                     static_cast<int>(row0) + static_cast<int>(cta_rank) * LOAD_N);
+        // ONE thread runs the whole loop (no per-tile elect / reconvergence): a tile costs a barrier wait, an expect_tx
+        // and a bulk copy
+        if (!kOneThread || lane == 0) {
+            uint32_t slot = 0, sph = 0, item_no = 0;
+            for (int64_t item = unit; item < items; item += units, ++item_no) {
+                const int64_t qtile = item % a.q_tiles;
+                const int part = static_cast<int>(item / a.q_tiles);
+                const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
+                const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+                const uint32_t ntiles = static_cast<uint32_t>((row_end - row_begin + tile_step - 1) / tile_step);
+                const uint32_t ab = item_no & 1u;
+                if (item_no >= 2) mbar_wait(&afree_bar[ab], ((item_no >> 1) - 1u) & 1u);  // MMAs of item_no - 2 are done
+                if (kOneThread || elect_one()) {
+                    if (leader) mbar_expect_tx(&afull_bar[ab], kCtas * kASlotBytes);
+                    klf_tma(&map_q, smem_u32(&afull_bar[ab]), abuf_addr + ab * kASlotBytes, 0,
+                            static_cast<int>(qtile * kTileQK) + static_cast<int>(cta_rank) * kBlockM);
                 }
-                __syncwarp();
-                if (++slot == kSlotsK) {
-                    slot = 0;
-                    sph ^= 1;
+                if (!kOneThread) __syncwarp();
+                int row = static_cast<int>(row_begin) + static_cast<int>(cta_rank) * LOAD_N;
+                for (uint32_t j = 0; j < ntiles; ++j, row += static_cast<int>(tile_step)) {
+                    mbar_wait(&empty_bar[slot], sph ^ 1);
+                    if (kOneThread || elect_one()) {
+                        if (leader) mbar_expect_tx(&full_bar[slot], kCtas * SLOT);
+                        klf_tma(&map_c, smem_u32(&full_bar[slot]), ring_addr + slot * SLOT, 0, row);
+                    }
+                    if (!kOneThread) __syncwarp();
+                    if (++slot == kSlotsK) {
+                        slot = 0;
+                        sph ^= 1;
+                    }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA) ================================
-        if (leader) {
+        // ================================ MMA issuer (leader CTA): one thread ================================
+        if (leader && (!kOneThread || lane == 0)) {
             uint32_t slot = 0, sph = 0, as = 0, aph = 0, item_no = 0;
             for (int64_t item = unit; item < items; item += units, ++item_no) {
                 const int part = static_cast<int>(item / a.q_tiles);
                 const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
                 const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
+                const uint32_t ntiles = static_cast<uint32_t>((row_end - row_begin + tile_step - 1) / tile_step);
                 const uint32_t ab = item_no & 1u;
                 mbar_wait(&afull_bar[ab], (item_no >> 1) & 1u);
                 tc_fence_after();
                 const uint64_t a_desc = make_smem_desc(abuf_addr + ab * kASlotBytes, 512, 4);  // SW64: hi at +0, lo at +32 B
-                for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
+                const uint64_t b_desc0 = FMT == kFmtBf16x3 ? make_smem_desc(ring_addr, 512, 4)    // SW64 rows of 64 B
+                                                           : make_smem_desc(ring_addr, 256, 6);   // SW32 rows of 32 B
+                for (uint32_t j = 0; j < ntiles; ++j) {
                     mbar_wait(&tempty_bar[as], aph ^ 1);
                     mbar_wait(&full_bar[slot], sph);
                     tc_fence_after();
                     const uint32_t d = as * kBlockN;
-                    const uint32_t sbase = ring_addr + slot * SLOT;
-                    if (elect_one()) {
+                    const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((slot * SLOT) >> 4);
+                    if (kOneThread || elect_one()) {
                         if (FMT == kFmtBf16x3) {
-                            const uint64_t b_desc = make_smem_desc(sbase, 512, 4);
-                            umma_ss2(d, a_desc, b_desc, IDESC, 0u);          // v_hi . L_hi
-                            umma_ss2(d, a_desc, b_desc + 2, IDESC, 1u);      // v_hi . L_lo
-                            umma_ss2(d, a_desc + 2, b_desc, IDESC, 1u);      // v_lo . L_hi
+                            klf_mma(d, a_desc, b_desc, IDESC, 0u);           // v_hi . L_hi
+                            klf_mma(d, a_desc, b_desc + 2, IDESC, 1u);       // v_hi . L_lo
+                            klf_mma(d, a_desc + 2, b_desc, IDESC, 1u);       // v_lo . L_hi
                         } else {
-                            const uint64_t b_desc = make_smem_desc(sbase, 256, 6);  // SW32: rows of 32 B, 8-row atoms 256 B apart
-                            umma_ss2(d, a_desc, b_desc, IDESC, 0u);          // v_hi . L16
-                            if (FMT == kFmtF16x2) umma_ss2(d, a_desc + 2, b_desc, IDESC, 1u);  // v_lo . L16
+                            klf_mma(d, a_desc, b_desc, IDESC, 0u);           // v_hi . L16
+                            if (FMT == kFmtF16x2) klf_mma(d, a_desc + 2, b_desc, IDESC, 1u);  // v_lo . L16
                         }
-                        umma_commit_pair(&empty_bar[slot]);
-                        umma_commit_pair(&tfull_bar[as]);
+                        klf_commit(&empty_bar[slot]);
+                        klf_commit(&tfull_bar[as]);
                     }
-                    __syncwarp();
+                    if (!kOneThread) __syncwarp();
                     if (++slot == kSlotsK) {
                         slot = 0;
                         sph ^= 1;
@@ -309,25 +380,28 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                         aph ^= 1;
                     }
                 }
-                if (elect_one()) umma_commit_pair(&afree_bar[ab]);  // the query buffer may be reloaded (both CTAs)
-                __syncwarp();
+                if (kOneThread || elect_one()) klf_commit(&afree_bar[ab]);  // the query buffer may be reloaded (both CTAs)
+                if (!kOneThread) __syncwarp();
             }
         }
+        __syncwarp();
     } else {
         // ================================ epilogue: E warps per lane quadrant split the columns ================================
         const int w = warp - 2;
         const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-        const int e = w >> 2;              // 64-column slice of every tile
+        const int e = w >> 2;              // warp set: candidate buffer / group slot of this warp
+        const int ts = e / kCS, cs = e % kCS;  // tile stream, 64-column slice of the stream's tiles
         const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
-        const uint32_t tacc0 = pin(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + e * 64);  // this warp's lanes and columns
+        const uint32_t tacc0 = pin(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + cs * 64);  // this warp's lanes and columns
         const uint32_t tfull_a = pin(smem_u32(tfull_bar));
-        const uint32_t tempty_a = pin(smem_u32(tempty_bar) & kPeerBitMask);  // the leader CTA's barriers
+        const uint32_t tempty_a = pin(kPair ? smem_u32(tempty_bar) & kPeerBitMask : smem_u32(tempty_bar));  // the leader CTA's barriers
         float* my_stage = stage + w * 32 * 32 + lane;  // [column * 32]: bank == lane
-        uint32_t as = 0, aph = 0;
+        const uint32_t lane0 = pin(lane == 0 ? 1u : 0u);
+        uint32_t g = 0;  // running tile number of this pair over all its items (accumulator stage g mod kStages)
         for (int64_t item = unit; item < items; item += units) {
             const int64_t qtile = item % a.q_tiles;
             const int part = static_cast<int>(item / a.q_tiles);
-            const int64_t qrow = qtile * kTileQ + r_in_tile;
+            const int64_t qrow = qtile * kTileQK + r_in_tile;
             const bool valid = qrow < a.q;
             const int64_t row_begin = static_cast<int64_t>(part) * a.rows_per_part;
             const int64_t row_end = min(a.n, row_begin + a.rows_per_part);
@@ -354,11 +428,16 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
             }
             // ---- prepass state ----
             float gmax = -CUDART_INF_F;
-            int gleft = a.group_tiles, tg = 0;
-            uint32_t* gdst = PREPASS ? a.groupmax + (qtile * a.groups + static_cast<int64_t>(part) * a.groups_per_slab + e) * kTileQ + r_in_tile
+            int tg = 0;
+            uint32_t gbound = static_cast<uint32_t>(a.group_tiles);  // first tile (slab-local number) of the next tile group
+            uint32_t* gdst = PREPASS ? a.groupmax + (qtile * a.groups + static_cast<int64_t>(part) * a.groups_per_slab + e) * kTileQK + r_in_tile
                                      : nullptr;
 
-            for (int64_t row0 = row_begin; row0 < row_end; row0 += tile_step) {
+            const uint32_t ntiles = static_cast<uint32_t>((row_end - row_begin + tile_step - 1) / tile_step);
+            // first tile of this item that belongs to this warp's stream
+            for (uint32_t j = (static_cast<uint32_t>(ts) + kTS - (g % kTS)) % kTS; j < ntiles; j += kTS) {
+                const uint32_t gt = g + j;
+                const uint32_t as = gt % kStages, aph = (gt / kStages) & 1u;
                 mbar_wait_a(tfull_a + as * 8, aph);
                 tc_fence_after();
                 const uint32_t t_acc = tacc0 + as * kBlockN;
@@ -368,12 +447,7 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                 tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster_a(tempty_a + as * 8);  // the stage is free: everything below runs on registers
-                if (++as == kStages) {
-                    as = 0;
-                    aph ^= 1;
-                }
-                const int64_t rowc = row0 + e * 64;  // corpus row of v[0]
+                if (lane0) mbar_arrive_cluster_a(tempty_a + as * 8);  // the stage is free: everything below runs on registers
                 // four independent chains of 16 keys each (FMNMX3: two keys per instruction)
                 float ch[4];
 #pragma unroll
@@ -385,36 +459,38 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                 }
                 if (PREPASS) {
                     float m = fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3]));
-                    if (rowc + 64 > row_end) {  // ragged last tile: rows past the end were zero-filled by TMA (key 0 beats them all)
-                        m = -CUDART_INF_F;
+                    if (j + 1 == ntiles) {  // last tile of the slab: rows past the end were zero-filled by TMA (key 0 beats them all)
+                        const int64_t rowc = row_begin + static_cast<int64_t>(j) * tile_step + cs * 64;
+                        if (rowc + 64 > row_end) {
+                            m = -CUDART_INF_F;
 #pragma unroll
-                        for (int jj = 0; jj < 64; ++jj)
-                            if (rowc + jj < row_end) m = fmaxf(m, v[jj]);
+                            for (int jj = 0; jj < 64; ++jj)
+                                if (rowc + jj < row_end) m = fmaxf(m, v[jj]);
+                        }
                     }
-                    gmax = fmaxf(gmax, m);
-                    if (--gleft == 0 || row0 + tile_step >= row_end) {
-                        gdst[static_cast<int64_t>(tg) * kE * kTileQ] =
+                    while (j >= gbound) {  // tile j opens a later tile group: the finished ones get their (possibly empty) maximum
+                        gdst[static_cast<int64_t>(tg) * kE * kTileQK] =
                             (valid && gmax > -CUDART_INF_F) ? f2ord(__fsub_rn(gmax * INV, shift)) : 0u;
                         gmax = -CUDART_INF_F;
-                        gleft = a.group_tiles;
+                        gbound += static_cast<uint32_t>(a.group_tiles);
                         ++tg;
                     }
+                    gmax = fmaxf(gmax, m);
                     continue;
                 }
-                const float m0 = fmaxf(ch[0], ch[1]), m1 = fmaxf(ch[2], ch[3]);
-                if (__any_sync(0xffffffffu, fmaxf(m0, m1) >= thr_acc)) {
-                    // rare path: per 32-column half that holds a survivor of some lane, stage the chunk in this warp's
+                if (__any_sync(0xffffffffu, fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3])) >= thr_acc)) {
+                    // rare path: per 16-column quarter that holds a survivor of some lane, stage the quarter in this warp's
                     // shared-memory scratch with a survivor bit mask, then walk the set bits
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (!__any_sync(0xffffffffu, (h ? m1 : m0) >= thr_acc)) continue;
+                    for (int c = 0; c < 4; ++c) {
+                        if (!__any_sync(0xffffffffu, ch[c] >= thr_acc)) continue;
                         uint32_t mask = 0;
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            my_stage[jj * 32] = v[32 * h + jj];
-                            mask |= (v[32 * h + jj] >= thr_acc ? 1u : 0u) << jj;
+                        for (int jj = 0; jj < 16; ++jj) {
+                            my_stage[jj * 32] = v[16 * c + jj];
+                            mask |= (v[16 * c + jj] >= thr_acc ? 1u : 0u) << jj;
                         }
-                        const int64_t row_base = rowc + 32 * h;
+                        const int64_t row_base = row_begin + static_cast<int64_t>(j) * tile_step + cs * 64 + 16 * c;
                         while (mask) {
                             const int jj = __ffs(mask) - 1;
                             mask &= mask - 1;
@@ -440,9 +516,14 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                     }
                 }
             }
+            g += ntiles;
             if (PREPASS) {
-                // slabs shorter than the longest one (the last slab): the remaining group slots hold "no value"
-                for (; tg * kE < a.groups_per_slab; ++tg) gdst[static_cast<int64_t>(tg) * kE * kTileQ] = 0u;
+                // the group in progress, then "no value" for the group slots this warp's tiles never reached (short last slab)
+                for (; tg * kE < a.groups_per_slab; ++tg) {
+                    gdst[static_cast<int64_t>(tg) * kE * kTileQK] =
+                        (valid && gmax > -CUDART_INF_F) ? f2ord(__fsub_rn(gmax * INV, shift)) : 0u;
+                    gmax = -CUDART_INF_F;
+                }
                 continue;
             }
             a.cnt[slot_idx] = valid ? static_cast<uint32_t>(cnt) : 0u;
@@ -452,8 +533,11 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
-    if (warp == 1) tmem_dealloc_pair(tmem_base);
+    if constexpr (kPair) cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
+    if (warp == 1) {
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base);
+        else tmem_dealloc1(tmem_base);
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.clk) {
         unsigned long long ns1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
@@ -464,31 +548,39 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
 
 // k'-th largest group maximum per query -> gthr (0 = no threshold).  One CTA per query tile, one thread per query:
 // the group maxima are read coalesced ([group][256 rows]); the running best k' live in shared memory (column = thread).
-__global__ void __launch_bounds__(kTileQ) klf_group_threshold_kernel(const uint32_t* __restrict__ groupmax, int64_t q,
+__global__ void __launch_bounds__(kTileQK) klf_group_threshold_kernel(const uint32_t* __restrict__ groupmax, int64_t q,
                                                                      int groups, int kp, uint32_t* __restrict__ gthr) {
     extern __shared__ uint32_t top[];  // [kp][256]
     const int t = threadIdx.x;
-    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kTileQ + t;
-    const uint32_t* src = groupmax + static_cast<int64_t>(blockIdx.x) * groups * kTileQ + t;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kTileQK + t;
+    const uint32_t* src = groupmax + static_cast<int64_t>(blockIdx.x) * groups * kTileQK + t;
     uint32_t minv = 0xFFFFFFFFu;
     int minpos = 0, have = 0;
-    for (int g = 0; g < groups; ++g) {
-        const uint32_t v = src[static_cast<int64_t>(g) * kTileQ];
-        if (have < kp) {
-            top[have * kTileQ + t] = v;
-            if (v < minv) {
-                minv = v;
-                minpos = have;
-            }
-            ++have;
-        } else if (v > minv) {
-            top[minpos * kTileQ + t] = v;
-            minv = 0xFFFFFFFFu;
-            for (int i = 0; i < kp; ++i) {
-                const uint32_t u = top[i * kTileQ + t];
-                if (u < minv) {
-                    minv = u;
-                    minpos = i;
+    constexpr int kBatch = 8;  // independent loads in flight per thread (the insertion logic below is a dependent chain)
+    for (int g0 = 0; g0 < groups; g0 += kBatch) {
+        uint32_t vb[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) vb[u] = g0 + u < groups ? __ldcs(src + static_cast<int64_t>(g0 + u) * kTileQK) : 0u;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (g0 + u >= groups) break;
+            const uint32_t v = vb[u];
+            if (have < kp) {
+                top[have * kTileQK + t] = v;
+                if (v < minv) {
+                    minv = v;
+                    minpos = have;
+                }
+                ++have;
+            } else if (v > minv) {
+                top[minpos * kTileQK + t] = v;
+                minv = 0xFFFFFFFFu;
+                for (int i = 0; i < kp; ++i) {
+                    const uint32_t u2 = top[i * kTileQK + t];
+                    if (u2 < minv) {
+                        minv = u2;
+                        minpos = i;
+                    }
                 }
             }
         }
@@ -523,13 +615,13 @@ static int launch_klf_mode(const KlfLaunch& fl, const KlfArgs& fa, cudaStream_t 
     CUtensorMap map_q, map_c;
     memset(&map_q, 0, sizeof map_q);
     memset(&map_c, 0, sizeof map_c);
-    const int64_t q_pad = fl.q_tiles * kTileQ;
+    const int64_t q_pad = fl.q_tiles * kTileQK;
     int rc = encode_2d_bf16(&map_q, fl.apack, 32, q_pad, 32, kBlockM, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     if (FMT == kFmtBf16x3)
-        rc = encode_2d_bf16(&map_c, fl.corpus->klpack, RADAR_KLPACK, fl.corpus->n, RADAR_KLPACK, kBlockN / 2, CU_TENSOR_MAP_SWIZZLE_64B);
+        rc = encode_2d_bf16(&map_c, fl.corpus->klpack, RADAR_KLPACK, fl.corpus->n, RADAR_KLPACK, kBlockN / kCtas, CU_TENSOR_MAP_SWIZZLE_64B);
     else
-        rc = encode_2d_bf16(&map_c, fl.corpus->kl16, kObsPad, fl.corpus->n, kObsPad, kBlockN / 2, CU_TENSOR_MAP_SWIZZLE_32B);
+        rc = encode_2d_bf16(&map_c, fl.corpus->kl16, kObsPad, fl.corpus->n, kObsPad, kBlockN / kCtas, CU_TENSOR_MAP_SWIZZLE_32B);
     if (rc) return rc;
     RADAR_CUDA_CHECK(cudaFuncSetAttribute(klf_kernel<FMT, PREPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem_bytes(FMT))));
@@ -537,13 +629,13 @@ static int launch_klf_mode(const KlfLaunch& fl, const KlfArgs& fa, cudaStream_t 
     int64_t units = fl.units < 1 ? 1 : fl.units;
     if (units > items) units = items;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
+    cfg.gridDim = dim3(static_cast<unsigned>(units * kCtas));
     cfg.blockDim = dim3(kThreadsK);
     cfg.dynamicSmemBytes = smem_bytes(FMT);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = kCtas;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -562,7 +654,7 @@ static int launch_klf_fmt(const KlfLaunch& fl, const KlfArgs& fa, cudaStream_t s
 // pack -> [prepass -> thresholds] -> filter.  The profiled span (ev_start .. ev_stop) covers prepass, threshold selection
 // and the real pass.
 static int launch_kl_filter(KlfLaunch& fl, cudaStream_t st, int* launches) {
-    const int64_t q_pad = fl.q_tiles * kTileQ;
+    const int64_t q_pad = fl.q_tiles * kTileQK;
     const size_t shift_off = (sizeof(uint16_t) * static_cast<size_t>(q_pad) * 32 + 255) / 256 * 256;
     float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(fl.apack) + shift_off);
     if (fl.fmt == kFmtBf16x3) {
@@ -599,8 +691,8 @@ static int launch_kl_filter(KlfLaunch& fl, cudaStream_t st, int* launches) {
         rc = launch_klf_fmt<true>(fl, fp, st);
         if (rc) return rc;
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(klf_group_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              static_cast<int>(sizeof(uint32_t) * kMaxKpPrepass * kTileQ)));
-        klf_group_threshold_kernel<<<static_cast<unsigned>(fl.q_tiles), kTileQ, sizeof(uint32_t) * fl.kp * kTileQ, st>>>(
+                                              static_cast<int>(sizeof(uint32_t) * kMaxKpPrepass * kTileQK)));
+        klf_group_threshold_kernel<<<static_cast<unsigned>(fl.q_tiles), kTileQK, sizeof(uint32_t) * fl.kp * kTileQK, st>>>(
             fl.groupmax, fl.q, fl.groups, fl.kp, fl.gthr);
         RADAR_CUDA_CHECK(cudaGetLastError());
         fa.gthr_init = 1;

@@ -117,9 +117,15 @@ static bool tc_supported(const radar_corpus_t* c, int mode, const DeviceInfo& di
 }
 
 // filter arithmetic of the KL-only tensor-core paths: what the caller asked for, else what the corpus carries
-static int resolve_kl_fmt(const radar_corpus_t* c, const radar_search_params_t* p, int* fmt) {
+// AUTO: the many-queries filter is select-bound, not tensor- or bandwidth-bound, so the arithmetic with the tightest error
+// bound (bf16 hi/lo x 3: fewest candidates per query) is the fastest there; the HBM-bound stream path prefers the 32-byte
+// fp16 rows (prefer_f16)
+static int resolve_kl_fmt(const radar_corpus_t* c, const radar_search_params_t* p, bool prefer_f16, int* fmt) {
     switch (p->kl_variant) {
-        case RADAR_KL_AUTO: *fmt = c->kl16 ? klf::kFmtF16x2 : klf::kFmtBf16x3; break;
+        case RADAR_KL_AUTO:
+            if (prefer_f16) *fmt = c->kl16 ? klf::kFmtF16x2 : klf::kFmtBf16x3;
+            else *fmt = c->klpack ? klf::kFmtBf16x3 : klf::kFmtF16x2;
+            break;
         case RADAR_KL_BF16X3: *fmt = klf::kFmtBf16x3; break;
         case RADAR_KL_F16X1: *fmt = klf::kFmtF16x1; break;
         case RADAR_KL_F16X2: *fmt = klf::kFmtF16x2; break;
@@ -255,7 +261,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         plan_parts(pl->q_tiles, c->n, kScanTC, sms, 2, &pl->parts, &pl->rows_per_part);
     } else {
         if (p->mode == RADAR_MODE_KL && !legacy_kl) {
-            int rc = resolve_kl_fmt(c, p, &pl->kl_fmt);
+            int rc = resolve_kl_fmt(c, p, false, &pl->kl_fmt);
             if (rc) return rc;
             pl->klf = 1;
             pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl_fmt(p->k, pl->kl_fmt);
@@ -271,9 +277,9 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
-        pl->tile_q = tc::kTileQ;
+        pl->tile_q = pl->klf ? klf::kTileQK : tc::kTileQ;
         pl->q_tiles = ceil_div64(q, pl->tile_q);
-        int units = sms / 2;  // one CTA pair (tcgen05 cta_group::2) per two SMs
+        int units = (pl->klf && !klf::kPair) ? sms : sms / 2;  // one CTA pair (tcgen05 cta_group::2) per two SMs, or single CTAs
         if (units < 1) units = 1;
         if (units > tc::kMaxUnits) units = tc::kMaxUnits;
         pl->units = units;
@@ -296,9 +302,9 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         // KL with many queries over a small corpus: the cold-start survivors (~k' ln n per query) cost more than a second
         // (partial) sweep of the cheap KL contraction, so a prepass over every tile_stride-th tile collects group maxima
         // and the real pass starts from near-exact thresholds (kl_filter.cuh).  About 512 groups per query.
-        if (pl->klf && c->n <= (2ll << 20) && pl->q_tiles >= 8 && pl->kp <= klf::kMaxKpPrepass) {
+        if (pl->klf && c->n <= (2ll << 20) && pl->q_tiles * pl->tile_q >= 2048 && pl->kp <= klf::kMaxKpPrepass) {
 #ifndef RADAR_KLF_PREPASS_STRIDE
-#define RADAR_KLF_PREPASS_STRIDE 2
+#define RADAR_KLF_PREPASS_STRIDE 3
 #endif
             const int64_t stride = RADAR_KLF_PREPASS_STRIDE;
             const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, klf::kBlockN), stride);
@@ -380,8 +386,7 @@ static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_
     FinalArgs g{};
     g.sel = fb_sel; g.R = k; g.k = k; g.mode = mode; g.sort = 0; g.qmap = ulist; g.nq_dev = ucount;
     g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx; g.out_packed = out_packed;
-    final_kernel<<<static_cast<unsigned>(q_max), kFinalThreads, 0, st>>>(g);
-    RADAR_CUDA_CHECK(cudaGetLastError());
+    RADAR_CUDA_CHECK(launch_final(g, q_max, st));
     return RADAR_OK;
 }
 
@@ -652,8 +657,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         FinalArgs f{};
         f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 0; f.qmap = nullptr;
         f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx; f.out_packed = out_packed;
-        final_kernel<<<static_cast<unsigned>(q), kFinalThreads, 0, st>>>(f);
-        RADAR_CUDA_CHECK(cudaGetLastError());
+        RADAR_CUDA_CHECK(launch_final(f, q, st));
         ++launches;
     } else {
         const bool certify = params->precision == RADAR_PREC_FP32;
@@ -707,8 +711,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         if (certify) {
             f.bound = bound; f.qerr = qerr; f.uncert_count = ucount; f.uncert_list = ulist;
         }
-        final_kernel<<<static_cast<unsigned>(q), kFinalThreads, 0, st>>>(f);
-        RADAR_CUDA_CHECK(cudaGetLastError());
+        RADAR_CUDA_CHECK(launch_final(f, q, st));
         ++launches;
         if (certify) {
             rc = launch_exact_rerun(corpus, queries, params->mode, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,

@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* 
     // the slabs' buffers stream through a kCandCap-entry working set; whenever it fills up the register radix
     // select keeps the best R (everything it drops has key <= the returned R-th key)
     int fill = 0;
+    uint32_t cnt_l = 0;  // counts of 32 slabs at a time, one per lane: the per-slab loop below never waits for a count
     for (int p = 0; p < parts; ++p) {
-        const int c = static_cast<int>(cnt[qi * parts + p]);
+        if ((p & 31) == 0) cnt_l = p + lane < parts ? cnt[qi * parts + p + lane] : 0u;
+        const int c = static_cast<int>(__shfl_sync(0xffffffffu, cnt_l, p & 31));
         const uint64_t* src = cand + (qi * parts + p) * cap;
         int done = 0;
         while (done < c) {
@@ -485,6 +487,56 @@ __global__ void __launch_bounds__(kFinalThreads) final_kernel(const FinalArgs a)
             a.uncert_list[slot] = static_cast<uint32_t>(qid);
         }
     }
+}
+
+// R <= 32: one WARP per query (a CTA per query is mostly launch overhead when R is a few dozen entries): every lane
+// holds one composite, its rank is the number of better ones (composites are distinct; empty slots rank by lane).
+constexpr int kFinalWarps = 8;
+
+__global__ void __launch_bounds__(kFinalWarps * 32) final_warp_kernel(const FinalArgs a, int64_t nq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kFinalWarps + warp;
+    if (a.nq_dev) nq = min(nq, static_cast<int64_t>(*a.nq_dev));
+    if (qi >= nq) return;  // warp-uniform
+    const uint64_t c = lane < a.R ? a.sel[qi * a.R + lane] : 0ull;
+    int rank = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const uint64_t o = __shfl_sync(0xffffffffu, c, j);
+        rank += (o > c || (o == c && j < lane)) ? 1 : 0;
+    }
+    const int64_t qid = a.qmap ? a.qmap[qi] : qi;
+    if (rank < a.k) {
+        float sc;
+        int64_t id;
+        if (c != 0ull) {
+            sc = api_score_from_key(a.mode, composite_key(c));
+            id = static_cast<int64_t>(composite_row(c)) + a.idx_offset;
+        } else {
+            sc = a.mode == RADAR_MODE_KL ? CUDART_INF_F : -CUDART_INF_F;
+            id = -1;
+        }
+        a.out_scores[qid * a.k + rank] = sc;
+        a.out_idx[qid * a.k + rank] = id;
+        if (a.out_packed) a.out_packed[qid * a.k + rank] = c != 0ull ? packed_global(c, a.idx_offset) : 0ull;
+    }
+    if (a.bound && rank == a.k - 1) {  // exactly one lane holds the k-th best entry
+        const float b = a.bound[qi];
+        bool ok = true;
+        if (b > -CUDART_INF_F) ok = (c != 0ull) && (b + a.qerr[qid] < composite_key(c));
+        if (!ok) {
+            const uint32_t slot = atomicAdd(a.uncert_count, 1u);
+            a.uncert_list[slot] = static_cast<uint32_t>(qid);
+        }
+    }
+}
+
+static inline cudaError_t launch_final(const FinalArgs& a, int64_t nq, cudaStream_t st) {
+    if (a.R <= 32 && a.k <= 32)
+        final_warp_kernel<<<static_cast<unsigned>((nq + kFinalWarps - 1) / kFinalWarps), kFinalWarps * 32, 0, st>>>(a, nq);
+    else
+        final_kernel<<<static_cast<unsigned>(nq), kFinalThreads, 0, st>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------
