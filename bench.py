@@ -610,6 +610,8 @@ class Bench:
         except (OSError, ValueError):
             pass
         roof["kernel"] = KERNEL_NAMES.get(stats.algo_used, str(stats.algo_used))
+        if mode == "kl" and stats.algo_used == 2:
+            roof["kernel"] = "klf_kernel"  # the dedicated many-queries KL filter (csrc/kl_filter.cuh)
         roof["kernel_ms"] = kern_ms_avg
         roof["kernel_span"] = ("prepass + threshold selection + filter" if (mode == "kl" and stats.algo_used == 2)
                                else "one launch")

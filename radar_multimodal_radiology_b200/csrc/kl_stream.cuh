@@ -27,32 +27,56 @@
 #include "common.cuh"
 #include "scan_kernels.cuh"
 #include "tc_filter.cuh"
+#include "kl_filter.cuh"
 
 namespace radar {
 namespace kls {
 
 using namespace tc;  // PTX wrappers, descriptors, cluster helpers
+using klf::kFmtBf16x3;
+using klf::kFmtF16x1;
+using klf::kFmtF16x2;
 
 constexpr int kTileRows = 512;          // corpus rows per super-tile: 256 per CTA = two M = 256 MMA sub-tiles
 constexpr int kSubRows = 256;           // corpus rows per MMA (128 per CTA)
-constexpr int kSlots = 8;               // smem ring slots of 16 KB (256 rows x 64 B) per CTA
-constexpr int kSlotBytes = 256 * 64;
+constexpr int kSlots = 8;               // smem ring slots per CTA: 256 rows x 64 B ([hi|lo] bf16 table) or x 32 B (fp16 table)
+__host__ __device__ constexpr int slot_bytes(int fmt) { return 256 * klf::row_bytes(fmt); }
 constexpr int kMaxN = 256;              // queries per launch (MMA N)
-constexpr int kStreamThreads = 352;     // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 epilogue sets (alternating super-tiles),
+#ifndef RADAR_KLS_ISSUERS
+#define RADAR_KLS_ISSUERS 2
+#endif
+#ifndef RADAR_KLS_DEFER
+#define RADAR_KLS_DEFER 0
+#endif
+// park a pooled append until the thread's next visit of the rare path instead of waiting ~700 cycles for its slot number.
+// Measured: SLOWER (0.125 -> 0.151 ms on kl_latency) -- entries reach the pool late, refreshes see fewer of them, thresholds
+// tighten later and more cases survive.  Kept as a build option.
+constexpr bool kDeferAppends = RADAR_KLS_DEFER != 0;
+constexpr int kIssuers = RADAR_KLS_ISSUERS;  // MMA issuer warps (warp 1 and warp 11) taking alternate super-tiles
+constexpr int kStreamThreads = 384;     // warp 0 TMA, warps 1 / 11 MMA, warps 2-5 / 6-9 epilogue sets (alternating super-tiles),
                                         // warp 10 threshold refresher
-constexpr int kRefreshEvery = 64;       // appends of a query between threshold refresh attempts
-constexpr int kThrReload = 4;           // super-tiles between reloads of the published thresholds
+#ifndef RADAR_KLS_REFRESH_EVERY
+#define RADAR_KLS_REFRESH_EVERY 64
+#endif
+#ifndef RADAR_KLS_RELOAD
+#define RADAR_KLS_RELOAD 4
+#endif
+#ifndef RADAR_KLS_MAX_SAMPLE
+#define RADAR_KLS_MAX_SAMPLE 1024
+#endif
+constexpr int kRefreshEvery = RADAR_KLS_REFRESH_EVERY;  // appends of a query between threshold refresh attempts
+constexpr int kThrReload = RADAR_KLS_RELOAD;            // super-tiles between reloads of the published thresholds
 constexpr int kMinRows = 1 << 16;       // smaller corpora use the general path
 constexpr int kBootThreads = 256;
 constexpr int kBootRows = 256;          // rows of one sample tile
-constexpr int kMaxSample = 1024;
+constexpr int kMaxSample = RADAR_KLS_MAX_SAMPLE;  // sample tiles of the boot pass (k'-th largest tile maximum = first threshold)
 
 __host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one query's pooled buffer
     int c = (1 << 20) / n_pad;
     return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
 }
 inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
-    int64_t s = 32768 / n_pad;
+    int64_t s = (32ll * kMaxSample) / n_pad;
     if (s < 256) s = 256;
     if (s > kMaxSample) s = kMaxSample;
     return static_cast<int>(s < boot_tiles ? s : boot_tiles);
@@ -173,7 +197,7 @@ struct StreamArgs {
     int reload;                  // super-tiles (of one epilogue set) between reloads of the published thresholds
 };
 
-constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * kSlotBytes + 128 * 64 /*queries*/ +
+constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * slot_bytes(kFmtBf16x3) + 128 * 64 /*queries*/ +
                                     8 * 32 * 32 * sizeof(float) /*chunk staging*/ + 8 * kMaxN * sizeof(float) /*thresholds*/ +
                                     kMaxN * sizeof(float) /*entropy*/ + kCandCap * sizeof(uint64_t) /*refresh scratch*/ +
                                     1024 /*barriers + refresh requests*/;
@@ -243,13 +267,20 @@ __device__ __noinline__ void refresh_threshold(const StreamArgs& a, int qi, uint
     __syncwarp();
 }
 
+// FMT (klf::kFmt*): bf16 hi/lo x 3 products on klpack (64 B rows), or fp16 x 1 / x 2 products on kl16 (32 B rows: half
+// the HBM bytes per case); the fp16 accumulators are scaled by 2^24 (kl_filter.cuh), thresholds are compared in scaled units
+template <int FMT>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_constant__ CUtensorMap map_q,
                  const StreamArgs a) {
+    constexpr int kSlotBytes = slot_bytes(FMT);
+    constexpr int ROW_B = klf::row_bytes(FMT);
+    constexpr float SCALE = FMT == kFmtBf16x3 ? 1.0f : klf::kAccScale;
+    constexpr float INV = FMT == kFmtBf16x3 ? 1.0f : klf::kAccInv;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = smem;                                                        // [kSlots][16 KB]
-    uint8_t* qtile = ring + kSlots * kSlotBytes;                                 // [n_pad/2 rows][64 B], SW64
+    uint8_t* qtile = ring + kSlots * slot_bytes(kFmtBf16x3);                     // [n_pad/2 rows][64 B], SW64
     float* stage = reinterpret_cast<float*>(qtile + 128 * 64);                   // [8 warps][32 cols][32 lanes]
     float* thr_s = stage + 8 * 32 * 32;                                          // [8 warps][kMaxN] accumulator units
     float* h_s = thr_s + 8 * kMaxN;                                              // [kMaxN]
@@ -270,7 +301,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     const int64_t unit = blockIdx.x >> 1, units = gridDim.x >> 1;
     const int N = a.n_pad;
     const int spairs = kTmemCols / (2 * N);  // accumulator stage pairs (1 .. 8)
-    const uint32_t idesc = make_idesc_mn(kSubRows, N);
+    const uint32_t idesc = FMT == kFmtBf16x3 ? make_idesc_mn(kSubRows, N) : klf::make_idesc_f16_mn(kSubRows, N);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_kl);
@@ -321,40 +352,49 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 sph ^= 1;
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA): 6 MMAs per super-tile ================================
-        if (leader) {
+    } else if (warp == 1 || warp == 11) {
+        // ================================ MMA issuers (leader CTA) ================================
+        // A super-tile costs its issuer two barrier waits, the MMAs and two commits -- several hundred cycles of serial
+        // latency that has nothing to do with the tensor pipe.  Two issuer warps take alternate super-tiles (tcgen05.commit
+        // tracks the MMAs of the issuing thread, so each warp signals exactly its own tiles); slots and stage pairs are
+        // revisited by the same issuer (their counts are even), which keeps the parity waits sound.  A single stage pair
+        // (256 queries) is shared by consecutive tiles: one issuer only.
+        const uint32_t ii = warp == 1 ? 0u : 1u;
+        const uint32_t nissue = (kIssuers > 1 && spairs > 1) ? 2u : 1u;
+        if (leader && ii < nissue) {
             mbar_wait(qfull_bar, 0);
             tc_fence_after();
             const uint64_t bdesc = make_smem_desc(smem_u32(qtile), 512, 4);
-            uint32_t slot = 0, sph = 0, sp = 0, aph = 0;
-            for (int64_t t = unit; t < a.tiles; t += units) {
+            const uint32_t sp_mask = static_cast<uint32_t>(spairs) - 1u, sp_shift = 31u - __clz(static_cast<uint32_t>(spairs));
+            for (uint32_t j = ii;; j += nissue) {
+                const int64_t t = unit + static_cast<int64_t>(j) * units;
+                if (t >= a.tiles) break;
+                const uint32_t slot = j % kSlots, sph = (j / kSlots) & 1u;
+                const uint32_t sp = j & sp_mask, aph = (j >> sp_shift) & 1u;
                 mbar_wait(&tempty_bar[sp], aph ^ 1);
                 mbar_wait(&full_bar[slot], sph);
                 tc_fence_after();
-                const uint64_t adesc = make_smem_desc(smem_u32(ring + slot * kSlotBytes), 512, 4);
+                const uint64_t adesc = FMT == kFmtBf16x3 ? make_smem_desc(smem_u32(ring + slot * kSlotBytes), 512, 4)   // SW64
+                                                         : make_smem_desc(smem_u32(ring + slot * kSlotBytes), 256, 6);  // SW32
                 const uint32_t d0 = static_cast<uint32_t>(sp * 2 * N);
                 if (elect_one()) {
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {  // rows [sub*128, sub*128+128) of each CTA's box
-                        const uint64_t ad = adesc + static_cast<uint64_t>((sub * 128 * 64) >> 4);
+                        const uint64_t ad = adesc + static_cast<uint64_t>((sub * 128 * ROW_B) >> 4);
                         const uint32_t d = d0 + static_cast<uint32_t>(sub * N);
-                        umma_ss_pair(d, ad, bdesc, idesc, 0u);      // L_hi . v_hi
-                        umma_ss_pair(d, ad + 2, bdesc, idesc, 1u);  // L_lo . v_hi
-                        umma_ss_pair(d, ad, bdesc + 2, idesc, 1u);  // L_hi . v_lo
+                        if (FMT == kFmtBf16x3) {
+                            umma_ss_pair(d, ad, bdesc, idesc, 0u);      // L_hi . v_hi
+                            umma_ss_pair(d, ad + 2, bdesc, idesc, 1u);  // L_lo . v_hi
+                            umma_ss_pair(d, ad, bdesc + 2, idesc, 1u);  // L_hi . v_lo
+                        } else {
+                            umma_ss_pair(d, ad, bdesc, idesc, 0u);      // L16 . v_hi
+                            if (FMT == kFmtF16x2) umma_ss_pair(d, ad, bdesc + 2, idesc, 1u);  // L16 . v_lo
+                        }
                     }
                     umma_commit_pair(&empty_bar[slot]);
                     umma_commit_pair(&tfull_bar[sp]);
                 }
                 __syncwarp();
-                if (++slot == kSlots) {
-                    slot = 0;
-                    sph ^= 1;
-                }
-                if (++sp == static_cast<uint32_t>(spairs)) {
-                    sp = 0;
-                    aph ^= 1;
-                }
             }
         }
     } else if (warp == 10) {
@@ -407,30 +447,53 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                     // a few ulps below fl(key + H): fl(fl(acc - H) + H) may round above acc, and cases tied with the
                     // threshold must not be lost (a lower threshold is always safe)
                     const float ta = __fadd_rn(tk, h_s[qi]);
-                    my_thr[qi] = qi < a.q ? (pending[i] ? ta - 4e-7f * (fabsf(ta) + fabsf(h_s[qi])) : -CUDART_INF_F) : CUDART_INF_F;
+                    my_thr[qi] = qi < a.q ? (pending[i] ? (ta - 4e-7f * (fabsf(ta) + fabsf(h_s[qi]))) * SCALE : -CUDART_INF_F)
+                                          : CUDART_INF_F;
                 }
             }
             __syncwarp();
         };
-        // rare path of one 32-case x 32-query chunk held in registers: stage it, walk the survivor bits
-        auto append_survivors = [&](const float (&v)[32], int cb, int64_t row, bool row_ok) {
+        // A pooled append needs a slot number from a global atomicAdd (~700 cycles).  The thread does not wait for it: the
+        // atomic is issued, the entry is parked in registers, and the store into the pool happens when the thread next
+        // comes through here (or at the end) -- by then the slot number has long arrived.  A slot that is still unwritten
+        // when a refresh looks at it reads as 0 ("empty"); the final pass rescans the whole pool, so nothing is lost.
+        uint32_t pend_slot = 0, pend_qi = 0;
+        uint64_t pend_comp = 0ull;  // 0 = nothing parked
+        auto flush_pending = [&]() {
+            if (pend_comp != 0ull) {
+                if (pend_slot < static_cast<uint32_t>(a.pool_cap))
+                    a.pool[static_cast<int64_t>(pend_qi) * a.pool_cap + pend_slot] = pend_comp;
+                if (((pend_slot + 1) % kRefreshEvery) == 0 && pend_slot + 1 >= static_cast<uint32_t>(a.kp))
+                    atomicOr(&refresh_req[pend_qi >> 5], 1u << (pend_qi & 31));
+                pend_comp = 0ull;
+            }
+        };
+        // rare path of one 32-case x 32-query chunk held in registers.  hits = which of the four predicate chains (query
+        // column mod 4) saw a survivor in this lane: only the columns of chains that fired in SOME lane are staged and
+        // compared again (typically 8 of 32), then the survivor bits are walked.
+        auto append_survivors = [&](const float (&v)[32], int cb, int64_t row, bool row_ok, uint32_t hits) {
             uint32_t mask = 0;
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                my_stage[c * 32] = v[c];
-                mask |= (v[c] >= my_thr[cb * 32 + c] ? 1u : 0u) << c;
+            for (int r = 0; r < 4; ++r) {
+                if (!__any_sync(0xffffffffu, (hits >> r) & 1u)) continue;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int c = 4 * c4 + r;
+                    my_stage[c * 32] = v[c];
+                    mask |= (v[c] >= my_thr[cb * 32 + c] ? 1u : 0u) << c;
+                }
             }
             if (!row_ok) mask = 0;
             while (mask) {
                 const int c = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const int qi = cb * 32 + c;
-                const float key = __fsub_rn(my_stage[c * 32], h_s[qi]);
-                const uint32_t slot = atomicAdd(a.gcnt + qi, 1u);
-                if (slot < static_cast<uint32_t>(a.pool_cap))
-                    a.pool[static_cast<int64_t>(qi) * a.pool_cap + slot] = make_composite(key, static_cast<uint32_t>(row));
-                if (((slot + 1) % kRefreshEvery) == 0 && slot + 1 >= static_cast<uint32_t>(a.kp))
-                    atomicOr(&refresh_req[qi >> 5], 1u << (qi & 31));
+                const float key = __fsub_rn(my_stage[c * 32] * INV, h_s[qi]);
+                flush_pending();
+                pend_slot = atomicAdd(a.gcnt + qi, 1u);
+                pend_qi = static_cast<uint32_t>(qi);
+                pend_comp = make_composite(key, static_cast<uint32_t>(row));
+                if (!kDeferAppends) flush_pending();
             }
             __syncwarp();
         };
@@ -483,11 +546,15 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 }
                 const bool hit0 = (g0 | g1 | g2 | g3) && ok0, hit1 = (h0 | h1 | h2 | h3) && ok1;
                 if (__any_sync(0xffffffffu, hit0 | hit1)) {
-                    if (__any_sync(0xffffffffu, hit0)) append_survivors(v0, cb, row0, ok0);
-                    if (__any_sync(0xffffffffu, hit1)) append_survivors(v1, cb, row1, ok1);
+                    if (__any_sync(0xffffffffu, hit0))
+                        append_survivors(v0, cb, row0, ok0, ok0 ? (g0 ? 1u : 0u) | (g1 ? 2u : 0u) | (g2 ? 4u : 0u) | (g3 ? 8u : 0u) : 0u);
+                    if (__any_sync(0xffffffffu, hit1))
+                        append_survivors(v1, cb, row1, ok1, ok1 ? (h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u) : 0u);
                 }
             }
         }
+        flush_pending();
+        __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(epi_done, 1u);
     }

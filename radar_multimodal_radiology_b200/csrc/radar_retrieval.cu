@@ -184,7 +184,7 @@ static void plan_parts_filter(int64_t q_tiles, int64_t n, int tile_rows, int uni
 }
 
 static bool kl_stream_supported(const radar_corpus_t* c, int64_t q, int mode, const DeviceInfo& di) {
-    return di.major == 10 && mode == RADAR_MODE_KL && c->klpack && c->logq16 && q >= 1 && q <= kls::kMaxN &&
+    return di.major == 10 && mode == RADAR_MODE_KL && (c->klpack || c->kl16) && c->logq16 && q >= 1 && q <= kls::kMaxN &&
            c->n >= kls::kMinRows;
 }
 
@@ -221,7 +221,12 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         return o;
     };
     if (algo == RADAR_ALGO_KL_STREAM) {
-        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl(p->k);
+        // AUTO: certified results want the tightest error bound (fewest exact re-runs, each a 10M-row scan): bf16 hi/lo x3;
+        // filter-only precision streams the 32-byte fp16 rows (half the HBM bytes, same speed: the path is not HBM-bound
+        // any more once the rows are this small)
+        int rc = resolve_kl_fmt(c, p, p->precision == RADAR_PREC_BF16, &pl->kl_fmt);
+        if (rc) return rc;
+        pl->kp = p->overfetch > 0 ? p->overfetch : auto_overfetch_kl_fmt(p->k, pl->kl_fmt);
         if (pl->kp < p->k) pl->kp = p->k;
         if (pl->kp > kCandSoft) pl->kp = kCandSoft;
         pl->R = pl->kp;
@@ -572,13 +577,21 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         const size_t shift_off = align_up(sizeof(uint16_t) * static_cast<size_t>(qp) * RADAR_KLPACK, 256);
         float* qshift = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(apack) + shift_off);
         RADAR_CUDA_CHECK(cudaMemsetAsync(zero, 0, pl.ks_zero_bytes, st));
-        tc::PackArgs pa{};
-        pa.q_emb = nullptr; pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp;
-        pa.d = corpus->d; pa.mode = RADAR_MODE_KL; pa.alpha = alpha; pa.oma = oma;
-        pa.emb_max_norm = corpus->emb_max_norm; pa.logq_max_abs = corpus->logq_max_abs;
-        tc::fill_col_max(corpus, pa.logq_col_max);
-        pa.apack = apack; pa.qshift = qshift; pa.qerr = qerr;
-        tc::query_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
+        if (pl.kl_fmt == klf::kFmtBf16x3) {
+            tc::PackArgs pa{};
+            pa.q_emb = nullptr; pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp;
+            pa.d = corpus->d; pa.mode = RADAR_MODE_KL; pa.alpha = alpha; pa.oma = oma;
+            pa.emb_max_norm = corpus->emb_max_norm; pa.logq_max_abs = corpus->logq_max_abs;
+            tc::fill_col_max(corpus, pa.logq_col_max);
+            pa.apack = apack; pa.qshift = qshift; pa.qerr = qerr;
+            tc::query_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
+        } else {
+            klf::KlPackArgs pa{};
+            pa.p16 = queries->p16; pa.entropy = queries->entropy; pa.q = q; pa.q_pad = qp; pa.fmt = pl.kl_fmt;
+            tc::fill_col_max(corpus, pa.logq_col_max);
+            pa.apack = apack; pa.qshift = qshift; pa.qerr = qerr;
+            klf::klf_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
+        }
         RADAR_CUDA_CHECK(cudaGetLastError());
         kls::BootArgs ba{};
         ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.qerr = qerr;
@@ -592,7 +605,10 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         CUtensorMap map_kl, map_q;
         memset(&map_kl, 0, sizeof map_kl);
         memset(&map_q, 0, sizeof map_q);
-        rc = tc::encode_2d_bf16(&map_kl, corpus->klpack, RADAR_KLPACK, corpus->n, RADAR_KLPACK, 256, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (pl.kl_fmt == klf::kFmtBf16x3)
+            rc = tc::encode_2d_bf16(&map_kl, corpus->klpack, RADAR_KLPACK, corpus->n, RADAR_KLPACK, 256, CU_TENSOR_MAP_SWIZZLE_64B);
+        else
+            rc = tc::encode_2d_bf16(&map_kl, corpus->kl16, kObsPad, corpus->n, kObsPad, 256, CU_TENSOR_MAP_SWIZZLE_32B);
         if (rc) return rc;
         rc = tc::encode_2d_bf16(&map_q, apack, RADAR_KLPACK, qp, RADAR_KLPACK, static_cast<uint32_t>(qp / 2),
                                 CU_TENSOR_MAP_SWIZZLE_64B);
@@ -602,7 +618,10 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         sa.pool_cap = pl.pool_cap; sa.qshift = qshift; sa.gthr = gthr; sa.gcnt = gcnt; sa.lock = lock;
         sa.processed = processed; sa.best_n = best_n; sa.best = best; sa.pool = pool;
         sa.reload = kls::kThrReload;  // measured: 4 beats 1, 2, 8, 16 on kl_latency (fresher thresholds vs reload cost)
-        RADAR_CUDA_CHECK(cudaFuncSetAttribute(kls::kl_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        auto stream_kernel = pl.kl_fmt == klf::kFmtBf16x3 ? kls::kl_stream_kernel<klf::kFmtBf16x3>
+                             : pl.kl_fmt == klf::kFmtF16x1 ? kls::kl_stream_kernel<klf::kFmtF16x1>
+                                                           : kls::kl_stream_kernel<klf::kFmtF16x2>;
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kls::kStreamSmemBytes)));
         int64_t units = pl.units;
         if (units > pl.tiles) units = pl.tiles;
@@ -619,7 +638,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (g_prof_start) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
-        RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kls::kl_stream_kernel, map_kl, map_q, sa));
+        RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, stream_kernel, map_kl, map_q, sa));
         if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));
         kls::StreamFinalArgs fa{};
         fa.p16 = queries->p16; fa.entropy = queries->entropy; fa.logq16 = corpus->logq16; fa.qerr = qerr; fa.gthr = gthr;

@@ -316,10 +316,25 @@ def test_kl_stream_fp32_is_bit_identical(dev, q, k):
     assert np.array_equal(i2, wi) and np.array_equal(s2, ws)
 
 
-def test_kl_stream_bf16_recall_and_canonical_scores(dev):
+@pytest.mark.parametrize("variant", ["bf16x3", "f16x1", "f16x2"])
+@pytest.mark.parametrize("q,k", [(1, 10), (32, 32), (100, 5), (200, 64)])
+def test_kl_stream_table_variants_fp32_bit_identical(dev, variant, q, k):
+    """The stream path on the [hi|lo] bf16 table (64 B per case) and on the fp16 table (32 B per case, one or two
+    products): certified fp32 results are bit-identical to the oracle in every arithmetic."""
+    p = make_problem(90001, q, d=64, seed=70 + q)
+    idx = _index(p, dev, precision="fp32", kl_variant=variant)
+    s, i = _search(idx, p, "kl", k)
+    assert idx.last_stats.algo_used == 3
+    ws, wi = _oracle(p, "kl", k)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    assert idx.last_stats.uncertified <= max(2, q // 3), (variant, idx.last_stats.uncertified, idx.last_stats.kprime)
+
+
+@pytest.mark.parametrize("variant", ["bf16x3", "f16x1", "f16x2"])
+def test_kl_stream_bf16_recall_and_canonical_scores(dev, variant):
     from oracle import c_oracle as co
     p = make_problem(300000, 64, d=64, seed=31)
-    idx = _index(p, dev, precision="bf16")
+    idx = _index(p, dev, precision="bf16", kl_variant=variant)
     for k in (10, 32):
         s, i = _search(idx, p, "kl", k)
         assert idx.last_stats.algo_used == 3 and idx.last_stats.uncertified == 0
