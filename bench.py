@@ -512,6 +512,7 @@ class Bench:
         def timed(fn, n_steps, kernel_events=False):
             """sum of per-step CUDA-event times (L2 flush between steps is outside the timed region), max over ranks"""
             total_ms, kern_ms = 0.0, 0.0
+            each = []
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -529,6 +530,7 @@ class Bench:
                 e1.record()
                 torch.cuda.synchronize()
                 total_ms += e0.elapsed_time(e1)
+                each.append(round(e0.elapsed_time(e1), 4))
                 if kernel_events:
                     ms = ctypes.c_float()
                     L.check(L.lib().radar_profile_kernel_ms(ctypes.byref(ms)), "radar_profile_kernel_ms")
@@ -539,6 +541,7 @@ class Bench:
                 t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 total_ms, kern_ms = t.tolist()
+            self.last_each = each  # this rank's per-step times of the last timed region
             return total_ms, kern_ms
 
         # ---- warm-up, then the timed regions -----------------------------------------------------------------
@@ -556,9 +559,11 @@ class Bench:
             for _ in range(2):
                 step_graph()
             total_ms, _ = timed(step_graph, steps)
+            each_ms = list(self.last_each)
             _, kern_ms = timed(step_device, steps, kernel_events=True)  # dominant kernel alone: eager launches
         else:
             total_ms, kern_ms = timed(step_device, steps, kernel_events=True)
+            each_ms = list(self.last_each)
         clocks = sampler.stop() if sampler is not None else None
         out_s, out_i = step_device(collect_stats=True)  # in-kernel clock of a launch made while the device is still under load
         stats = ri.last_stats
@@ -619,6 +624,7 @@ class Bench:
 
         rec = {
             "value": value, "unit": "queries/s", "ms_per_step": total_ms / steps, "steps": steps,
+            "ms_each_step_rank0": each_ms,
             "config": workload_config(args, name, wl, n_total, k, precision, graph_note),
             "e2e": e2e, "gpu_launches": launches_per_step[0] * steps, "roofline": roof,
             "search_stats": {"algo_used": stats.algo_used, "parts": stats.parts, "kprime": stats.kprime,

@@ -238,6 +238,16 @@ int radar_gather_bits(const uint16_t* table, int64_t n, const int64_t* idx, int6
 int radar_project_normalize(const float* x, const float* w, const float* bias, int64_t b, int in_dim,
                             int out_dim, float* y, void* stream);
 
+/* The same operator on the tensor pipe (tcgen05, bf16 hi/lo split of both operands, three products, fp32 accumulation:
+ * components within 1e-5 of the fp32 result): needs out_dim == 512 and in_dim % 32 == 0 (BiomedCLIP: 768 -> 512) and
+ * a scratch buffer of radar_project_workspace_bytes(b, in_dim, out_dim) bytes (0 = shape not supported: use
+ * radar_project_normalize).  Outputs (each nullable, not both): y fp32 [b,512]; y_bf16 [b,512] = bf16 RN of the
+ * normalised rows, i.e. the A-operand rows the DPR filter would otherwise pack from y. */
+size_t radar_project_workspace_bytes(int64_t b, int in_dim, int out_dim);
+int radar_project_normalize_tc(const float* x, const float* w, const float* bias, int64_t b, int in_dim,
+                               int out_dim, float* y, uint16_t* y_bf16, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

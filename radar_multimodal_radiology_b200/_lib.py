@@ -71,7 +71,7 @@ EXPORTS = [
     "radar_profile_enable", "radar_profile_kernel_ms", "radar_pack_embeddings",
     "radar_kl_prepare_corpus", "radar_kl_prepare_queries", "radar_search_workspace_bytes", "radar_search",
     "radar_merge_topk", "radar_merge_packed", "radar_rerank_overlap", "radar_gather_bits", "radar_project_normalize",
-    "radar_get_device",
+    "radar_get_device", "radar_project_workspace_bytes", "radar_project_normalize_tc",
 ]
 DEBUG_EXPORTS = ["radar_debug_filter_keys"]
 
@@ -138,6 +138,10 @@ def _declare(l, debug: bool):
                                     C.c_void_p, C.c_void_p]
     l.radar_project_normalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]
+    l.radar_project_workspace_bytes.restype = C.c_size_t
+    l.radar_project_workspace_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    l.radar_project_normalize_tc.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     l.radar_set_device.argtypes = [C.c_int]
     l.radar_get_device.argtypes = [C.POINTER(C.c_int)]
     l.radar_profile_enable.argtypes = [C.c_int]

@@ -12,6 +12,7 @@
 #include "tc_filter.cuh"
 #include "kl_filter.cuh"
 #include "kl_stream.cuh"
+#include "proj_gemm.cuh"
 
 namespace radar {
 
@@ -865,6 +866,31 @@ int radar_project_normalize(const float* x, const float* w, const float* bias, i
         x, w, bias, in_dim, out_dim, y);
     RADAR_CUDA_CHECK(cudaGetLastError());
     return RADAR_OK;
+}
+
+size_t radar_project_workspace_bytes(int64_t b, int in_dim, int out_dim) {
+    if (b < 0 || !proj::proj_tc_supported(in_dim, out_dim)) return 0;
+    return proj::proj_workspace_bytes(b, in_dim);
+}
+
+int radar_project_normalize_tc(const float* x, const float* w, const float* bias, int64_t b, int in_dim, int out_dim,
+                               float* y, uint16_t* y_bf16, void* workspace, size_t workspace_bytes, void* stream) {
+    RADAR_ARG_CHECK(x && w && (y || y_bf16) && b >= 0, "project_normalize_tc: bad arguments");
+    RADAR_ARG_CHECK(proj::proj_tc_supported(in_dim, out_dim), "project_normalize_tc: needs out_dim == 512 and in_dim %% 32 == 0");
+    if (b == 0) return RADAR_OK;
+    DeviceInfo di;
+    int rc = get_device_info(&di);
+    if (rc) return rc;
+    if (di.major != 10) {
+        set_error("project_normalize_tc needs an sm_100 device");
+        return RADAR_E_ARCH;
+    }
+    if (!workspace || workspace_bytes < proj::proj_workspace_bytes(b, in_dim)) {
+        set_error("project_normalize_tc: workspace too small: need %zu bytes, got %zu", proj::proj_workspace_bytes(b, in_dim),
+                  workspace_bytes);
+        return RADAR_E_WORKSPACE;
+    }
+    return proj::launch_proj_tc(x, w, bias, b, in_dim, y, y_bf16, workspace, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

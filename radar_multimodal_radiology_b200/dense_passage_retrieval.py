@@ -78,10 +78,9 @@ class CrossModalEmbedder(nn.Module):
             self.model_loaded = False
 
     def _project(self, feats: torch.Tensor, proj: nn.Linear) -> torch.Tensor:
-        feats = feats.to(self.device, torch.float32)
-        if feats.is_cuda:
-            return project_normalize(feats, proj.weight, proj.bias)  # fused Linear + normalise kernel
-        return torch.nn.functional.normalize(proj(feats), dim=-1)
+        if self.device.type != 'cuda':
+            raise RuntimeError("CrossModalEmbedder needs a CUDA device: the projection + normalise prologue has no CPU path")
+        return project_normalize(feats.to(self.device, torch.float32), proj.weight, proj.bias)  # fused tcgen05 GEMM + normalise
 
     @torch.no_grad()
     def encode_text(self, texts: List[str]) -> torch.Tensor:
@@ -184,6 +183,26 @@ class HybridRetriever(nn.Module):
             'negatives': retrieved[k:k + num_negatives],
             'positive_scores': scores[:k],
             'negative_scores': scores[k:k + num_negatives],
+        }
+
+
+    def retrieve_batch_with_hard_negatives(self, query_embeds: torch.Tensor, k: int = None, num_negatives: int = 3,
+                                           query_probs=None, mask=None) -> Dict[str, torch.Tensor]:
+        """Hard-negative mining for a whole batch (dpr.py:320-331 asks for ``k + num_negatives`` per query and slices):
+        ONE search for ``k + num_negatives`` results per query, split on the device -- ranks ``[0, k)`` are the
+        positives, ranks ``[k, k + num_negatives)`` the hard negatives.  CUDA tensors: ``positives`` int64[Q,k],
+        ``negatives`` int64[Q,n], ``positive_scores`` / ``negative_scores`` float32; no host synchronisation.  Like the
+        reference, fewer than ``k + num_negatives`` passages shrink the negatives first."""
+        if k is None:
+            k = self.config.num_retrieved
+        if not self.semantic_index or k <= 0:
+            raise RuntimeError("retrieve_batch_with_hard_negatives on an empty index")
+        scores, ids = self.retrieve_batch(query_embeds, k + num_negatives, query_probs=query_probs, mask=mask)
+        return {
+            'positives': ids[:, :k].contiguous(),
+            'negatives': ids[:, k:k + num_negatives].contiguous(),
+            'positive_scores': scores[:, :k].contiguous(),
+            'negative_scores': scores[:, k:k + num_negatives].contiguous(),
         }
 
 

@@ -604,15 +604,37 @@ def merge_packed(packed: torch.Tensor, k: int, mode: str) -> Tuple[torch.Tensor,
     return out_s, out_i
 
 
-def project_normalize(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """``F.normalize(F.linear(x, weight, bias), dim=-1)`` (dpr.py:246 / :263) as one CUDA kernel."""
+def project_normalize(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: str = "fp32",
+                      algo: str = "auto"):
+    """``F.normalize(F.linear(x, weight, bias), dim=-1)`` (dpr.py:246 / :263) as a fused CUDA operator.
+
+    ``algo`` "auto" / "tc": the tcgen05 GEMM (bf16 hi/lo split x 3 products, fp32 accumulation; components within 1e-5 of
+    fp32) when the shape allows (out features == 512, in features % 32 == 0 -- BiomedCLIP's 768 -> 512); "simt": the
+    CUDA-core kernel (any shape).  ``out``: "fp32" -> float32[B,512]; "bf16" -> the bfloat16 rows (the A-operand rows of
+    the DPR filter); "both" -> (fp32, bf16)."""
     if x.device.type != "cuda":
         raise RuntimeError("project_normalize runs on a CUDA device only")
+    if out not in ("fp32", "bf16", "both"):
+        raise ValueError("out must be 'fp32', 'bf16' or 'both'")
     x = x.contiguous().float()
     w = weight.detach().contiguous().float()
     b = None if bias is None else bias.detach().contiguous().float()
-    y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.float32, device=x.device)
+    rows, in_dim, out_dim = x.shape[0], x.shape[1], w.shape[0]
+    lib = L.lib()
     with L.device_guard(x.device):
-        L.check(L.lib().radar_project_normalize(L.ptr(x), L.ptr(w), L.ptr(b), x.shape[0], x.shape[1], w.shape[0],
-                                                L.ptr(y), L.current_stream_ptr(x.device)), "radar_project_normalize")
-    return y
+        ws_bytes = int(lib.radar_project_workspace_bytes(rows, in_dim, out_dim)) if algo in ("auto", "tc") else 0
+        if algo == "tc" and ws_bytes == 0:
+            raise ValueError("the tensor-core projection needs 512 output features and in features % 32 == 0")
+        if ws_bytes:
+            y = torch.empty((rows, out_dim), dtype=torch.float32, device=x.device) if out != "bf16" else None
+            yb = torch.empty((rows, out_dim), dtype=torch.bfloat16, device=x.device) if out != "fp32" else None
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
+            L.check(lib.radar_project_normalize_tc(L.ptr(x), L.ptr(w), L.ptr(b), rows, in_dim, out_dim, L.ptr(y), L.ptr(yb),
+                                                   L.ptr(ws), ws_bytes, L.current_stream_ptr(x.device)),
+                    "radar_project_normalize_tc")
+            ws.record_stream(torch.cuda.current_stream(x.device))
+            return y if out == "fp32" else (yb if out == "bf16" else (y, yb))
+        y = torch.empty((rows, out_dim), dtype=torch.float32, device=x.device)
+        L.check(lib.radar_project_normalize(L.ptr(x), L.ptr(w), L.ptr(b), rows, in_dim, out_dim, L.ptr(y),
+                                            L.current_stream_ptr(x.device)), "radar_project_normalize")
+    return y if out == "fp32" else (y.bfloat16() if out == "bf16" else (y, y.bfloat16()))

@@ -65,3 +65,24 @@ def topk_sets_match(ids_a, ids_b, scores_true_of_a, scores_true_of_b, tol):
             if abs(x - y) > tol:
                 bad += 1
     return bad
+
+
+def assert_topk_within_ties(ids, want_ids, true_scores, want_scores, tol, what=""):
+    """north_star: "top-k index lists identical except where tied scores fall within tolerance".
+
+    ``true_scores`` is the float64 ground-truth score MATRIX [Q,N] (API sign), ``want_ids`` / ``want_scores`` the golden
+    top-k of that matrix, ``tol`` a scalar or a [Q,k] array.  (1) every position where the returned id differs from the
+    golden one must hold a case whose TRUE score is within tol of the golden score at that rank (a swap inside a tie
+    band); (2) the two id SETS may differ only by cases whose true scores are within tol of each other
+    (:func:`topk_sets_match`).  Nothing else is tolerated -- in particular not "97 % of the ids agree"."""
+    import numpy as np
+    ids, want_ids = np.asarray(ids), np.asarray(want_ids)
+    tol_a = np.broadcast_to(np.asarray(tol, dtype=np.float64), ids.shape)
+    got_true = np.take_along_axis(true_scores, ids, axis=1)
+    mism = ids != want_ids
+    worst = np.abs(got_true - want_scores)[mism]
+    assert np.all(worst <= tol_a[mism] + 1e-12), f"{what}: {int((worst > tol_a[mism] + 1e-12).sum())} positions differ outside the tie band"
+    want_true = np.take_along_axis(true_scores, want_ids, axis=1)
+    bad = topk_sets_match(ids, want_ids, got_true, want_true, float(np.max(tol_a)))
+    assert bad == 0, f"{what}: {bad} set differences outside the tie band"
+    return int(mism.sum())

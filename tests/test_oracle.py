@@ -6,7 +6,7 @@ import pytest
 
 from oracle import c_oracle as co
 from oracle import retrieval_oracle as ro
-from conftest import make_problem
+from conftest import assert_topk_within_ties, make_problem
 
 
 def _prep(p, masked=True):
@@ -56,16 +56,17 @@ def test_golden_vectors_canonical_c_oracle(golden, k):
         scale = ro.kl_operand_scale_fp64(g["q_probs"], g["c_probs"], mask, normalize=normalize)
         tol = 1e-5 * np.take_along_axis(scale, want_i, axis=1)
         assert np.all(np.abs(s - want_s) <= tol + 1e-12)
-        assert np.mean(i == want_i) > 0.97  # KL near 0 cancels: ids may swap only inside the tolerance band
+        # KL near 0 cancels: ids may swap only inside the tolerance band (tie-aware comparison, not an agreement rate)
         true = ro.kl_matrix_fp64(g["q_probs"], g["c_probs"], mask, normalize=normalize)
-        got_true = np.take_along_axis(true, i, axis=1)
-        assert np.all(np.abs(got_true - want_s) <= 2 * tol + 1e-12)
+        assert_topk_within_ties(i, want_i, true, want_s, 2 * tol, f"{tag} k={k}")
     p16, ent = co.prepare_queries(g["q_probs"], g["mask"])
     for alpha in (0.0, 0.25, 0.5, 1.0):
         s, i = co.search(co.MODE_HYBRID, k, q_emb=g["q_emb"], p16=p16, entropy=ent, c_emb=g["c_emb"], logq16=logq,
                          alpha=alpha)
         tag = f"hyb_a{int(alpha * 100):03d}_k{k}"
-        assert np.mean(i == g[tag + "_i"]) > 0.97
+        true = ro.score_matrix_fp64(ro.MODE_HYBRID, q_emb=g["q_emb"], c_emb=g["c_emb"], q_probs=g["q_probs"],
+                                    c_probs=g["c_probs"], mask=g["mask"], alpha=alpha)
+        assert_topk_within_ties(i, g[tag + "_i"], true, g[tag + "_s"], 2e-4, tag)
         assert np.max(np.abs(s - g[tag + "_s"])) <= 2e-4
 
 
