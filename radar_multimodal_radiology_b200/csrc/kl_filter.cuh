@@ -56,10 +56,14 @@ constexpr bool kOneThread = RADAR_KLF_ONE_THREAD != 0;
 constexpr bool kPair = RADAR_KLF_PAIR != 0;  // CTA pairs (tcgen05 cta_group::2, M = 256) or single CTAs (M = 128, all hand-offs CTA-local)
 constexpr int kCtas = kPair ? 2 : 1;
 constexpr int kTileQK = kBlockM * kCtas;   // query rows per work tile
-constexpr int kCS = RADAR_KLF_CS;          // warps per lane quadrant that split the columns of one tile (64 columns each)
+#ifndef RADAR_KLF_CPW
+#define RADAR_KLF_CPW 1
+#endif
+constexpr int kCPW = RADAR_KLF_CPW;        // 64-column chunks a warp reads one after the other from each of its tiles
+constexpr int kCS = RADAR_KLF_CS;          // warps per lane quadrant that split the columns of one tile (64 kCPW columns each)
 constexpr int kTS = RADAR_KLF_TS;          // tile streams: tile g of a pair is filtered by the warps of stream g mod kTS
 constexpr int kE = kCS * kTS;              // epilogue warps per TMEM lane quadrant == candidate buffers per (query, slab)
-constexpr int kBlockN = 64 * kCS;          // corpus rows per tile (whole pair / CTA)
+constexpr int kBlockN = 64 * kCS * kCPW;   // corpus rows per tile (whole pair / CTA)
 constexpr int kStages = 512 / kBlockN > 8 ? 8 : 512 / kBlockN;  // accumulator stages
 constexpr int kThreadsK = 64 + 128 * kE;   // warp 0 TMA, warp 1 MMA + TMEM alloc, 4 E epilogue warps
 // a stream waits for "its" tile on an mbarrier PARITY, which is only sound when the previous phase of that barrier is
@@ -392,7 +396,7 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
         const int e = w >> 2;              // warp set: candidate buffer / group slot of this warp
         const int ts = e / kCS, cs = e % kCS;  // tile stream, 64-column slice of the stream's tiles
         const int r_in_tile = static_cast<int>(cta_rank) * kBlockM + quad * 32 + lane;
-        const uint32_t tacc0 = pin(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + cs * 64);  // this warp's lanes and columns
+        const uint32_t tacc0 = pin(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + cs * 64 * kCPW);  // this warp's lanes and columns
         const uint32_t tfull_a = pin(smem_u32(tfull_bar));
         const uint32_t tempty_a = pin(kPair ? smem_u32(tempty_bar) & kPeerBitMask : smem_u32(tempty_bar));  // the leader CTA's barriers
         float* my_stage = stage + w * 32 * 32 + lane;  // [column * 32]: bank == lane
@@ -441,33 +445,81 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                 mbar_wait_a(tfull_a + as * 8, aph);
                 tc_fence_after();
                 const uint32_t t_acc = tacc0 + as * kBlockN;
-                float v[64];
-                tmem_ld_x32(t_acc, v);
-                tmem_ld_x32(t_acc + 32, v + 32);
-                tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane0) mbar_arrive_cluster_a(tempty_a + as * 8);  // the stage is free: everything below runs on registers
-                // four independent chains of 16 keys each (FMNMX3: two keys per instruction)
-                float ch[4];
+                float tile_m = -CUDART_INF_F;  // prepass: maximum over this warp's columns of the tile
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float m = v[16 * c];
+                for (int cw = 0; cw < kCPW; ++cw) {
+                    const int col0 = (cs * kCPW + cw) * 64;  // first tile column of this chunk
+                    float v[64];
+                    tmem_ld_x32(t_acc + cw * 64, v);
+                    tmem_ld_x32(t_acc + cw * 64 + 32, v + 32);
+                    tmem_wait_ld();
+                    if (cw == kCPW - 1) {  // the stage is free once the last chunk is in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane0) mbar_arrive_cluster_a(tempty_a + as * 8);
+                    }
+                    // four independent chains of 16 keys each (FMNMX3: two keys per instruction)
+                    float ch[4];
 #pragma unroll
-                    for (int jj = 1; jj < 15; jj += 2) m = fmaxf(fmaxf(m, v[16 * c + jj]), v[16 * c + jj + 1]);
-                    ch[c] = fmaxf(m, v[16 * c + 15]);
-                }
-                if (PREPASS) {
-                    float m = fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3]));
-                    if (j + 1 == ntiles) {  // last tile of the slab: rows past the end were zero-filled by TMA (key 0 beats them all)
-                        const int64_t rowc = row_begin + static_cast<int64_t>(j) * tile_step + cs * 64;
-                        if (rowc + 64 > row_end) {
-                            m = -CUDART_INF_F;
+                    for (int c = 0; c < 4; ++c) {
+                        float m = v[16 * c];
 #pragma unroll
-                            for (int jj = 0; jj < 64; ++jj)
-                                if (rowc + jj < row_end) m = fmaxf(m, v[jj]);
+                        for (int jj = 1; jj < 15; jj += 2) m = fmaxf(fmaxf(m, v[16 * c + jj]), v[16 * c + jj + 1]);
+                        ch[c] = fmaxf(m, v[16 * c + 15]);
+                    }
+                    if (PREPASS) {
+                        float m = fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3]));
+                        if (j + 1 == ntiles) {  // last tile of the slab: rows past the end were zero-filled by TMA (key 0 beats them all)
+                            const int64_t rowc = row_begin + static_cast<int64_t>(j) * tile_step + col0;
+                            if (rowc + 64 > row_end) {
+                                m = -CUDART_INF_F;
+#pragma unroll
+                                for (int jj = 0; jj < 64; ++jj)
+                                    if (rowc + jj < row_end) m = fmaxf(m, v[jj]);
+                            }
+                        }
+                        tile_m = fmaxf(tile_m, m);
+                        continue;
+                    }
+                    if (__any_sync(0xffffffffu, fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3])) >= thr_acc)) {
+                        // rare path: per 16-column quarter that holds a survivor of some lane, stage the quarter in this warp's
+                        // shared-memory scratch with a survivor bit mask, then walk the set bits
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            if (!__any_sync(0xffffffffu, ch[c] >= thr_acc)) continue;
+                            uint32_t mask = 0;
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                my_stage[jj * 32] = v[16 * c + jj];
+                                mask |= (v[16 * c + jj] >= thr_acc ? 1u : 0u) << jj;
+                            }
+                            const int64_t row_base = row_begin + static_cast<int64_t>(j) * tile_step + col0 + 16 * c;
+                            while (mask) {
+                                const int jj = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const int64_t row = row_base + jj;
+                                if (row < row_end)
+                                    buf[cnt++] = make_composite(__fsub_rn(my_stage[jj * 32] * INV, shift), static_cast<uint32_t>(row));
+                            }
+                            __syncwarp();
+                            unsigned need = __ballot_sync(0xffffffffu, cnt > kCandSoft);
+                            while (need) {
+                                const int src_lane = __ffs(need) - 1;
+                                need &= need - 1;
+                                uint64_t* b = reinterpret_cast<uint64_t*>(
+                                    __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src_lane));
+                                const int n_src = __shfl_sync(0xffffffffu, cnt, src_lane);
+                                const float t = warp_compact(b, n_src, a.kp, lane);
+                                if (lane == src_lane) {
+                                    thr = t;
+                                    thr_acc = __fadd_rn(t, shift) * SCALE;  // own threshold: every kept key was fl(acc - shift)
+                                    cnt = a.kp;
+                                }
+                            }
                         }
                     }
+                }
+                if (PREPASS) {
                     while (j >= gbound) {  // tile j opens a later tile group: the finished ones get their (possibly empty) maximum
                         gdst[static_cast<int64_t>(tg) * kE * kTileQK] =
                             (valid && gmax > -CUDART_INF_F) ? f2ord(__fsub_rn(gmax * INV, shift)) : 0u;
@@ -475,45 +527,7 @@ klf_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CU
                         gbound += static_cast<uint32_t>(a.group_tiles);
                         ++tg;
                     }
-                    gmax = fmaxf(gmax, m);
-                    continue;
-                }
-                if (__any_sync(0xffffffffu, fmaxf(fmaxf(ch[0], ch[1]), fmaxf(ch[2], ch[3])) >= thr_acc)) {
-                    // rare path: per 16-column quarter that holds a survivor of some lane, stage the quarter in this warp's
-                    // shared-memory scratch with a survivor bit mask, then walk the set bits
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        if (!__any_sync(0xffffffffu, ch[c] >= thr_acc)) continue;
-                        uint32_t mask = 0;
-#pragma unroll
-                        for (int jj = 0; jj < 16; ++jj) {
-                            my_stage[jj * 32] = v[16 * c + jj];
-                            mask |= (v[16 * c + jj] >= thr_acc ? 1u : 0u) << jj;
-                        }
-                        const int64_t row_base = row_begin + static_cast<int64_t>(j) * tile_step + cs * 64 + 16 * c;
-                        while (mask) {
-                            const int jj = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const int64_t row = row_base + jj;
-                            if (row < row_end)
-                                buf[cnt++] = make_composite(__fsub_rn(my_stage[jj * 32] * INV, shift), static_cast<uint32_t>(row));
-                        }
-                        __syncwarp();
-                        unsigned need = __ballot_sync(0xffffffffu, cnt > kCandSoft);
-                        while (need) {
-                            const int src_lane = __ffs(need) - 1;
-                            need &= need - 1;
-                            uint64_t* b = reinterpret_cast<uint64_t*>(
-                                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src_lane));
-                            const int n_src = __shfl_sync(0xffffffffu, cnt, src_lane);
-                            const float t = warp_compact(b, n_src, a.kp, lane);
-                            if (lane == src_lane) {
-                                thr = t;
-                                thr_acc = __fadd_rn(t, shift) * SCALE;  // own threshold: every kept key was fl(acc - shift)
-                                cnt = a.kp;
-                            }
-                        }
-                    }
+                    gmax = fmaxf(gmax, tile_m);
                 }
             }
             g += ntiles;
