@@ -307,14 +307,18 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
         // KL with many queries over a small corpus: the cold-start survivors (~k' ln n per query) cost more than a second
         // (partial) sweep of the cheap KL contraction, so a prepass over every tile_stride-th tile collects group maxima
-        // and the real pass starts from near-exact thresholds (kl_filter.cuh).  About 512 groups per query.
+        // and the real pass starts from near-exact thresholds (kl_filter.cuh).  About 256 groups per query (measured: 512 groups
+        // tighten the thresholds a little and cost more in the threshold kernel than they save: 3.66 vs 3.60 ms per step).
         if (pl->klf && c->n <= (2ll << 20) && pl->q_tiles * pl->tile_q >= 2048 && pl->kp <= klf::kMaxKpPrepass) {
 #ifndef RADAR_KLF_PREPASS_STRIDE
 #define RADAR_KLF_PREPASS_STRIDE 3
 #endif
             const int64_t stride = RADAR_KLF_PREPASS_STRIDE;
             const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, klf::kBlockN), stride);
-            int64_t tgs = 512 / (static_cast<int64_t>(pl->parts) * klf::kE);
+#ifndef RADAR_KLF_GROUPS
+#define RADAR_KLF_GROUPS 256
+#endif
+            int64_t tgs = RADAR_KLF_GROUPS / (static_cast<int64_t>(pl->parts) * klf::kE);
             if (tgs > slab_tiles) tgs = slab_tiles;
             if (tgs < 1) tgs = 1;
             const int64_t gt = ceil_div64(slab_tiles, tgs);
