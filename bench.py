@@ -581,6 +581,12 @@ class Bench:
             # restore the device-resident queries (the e2e leg overwrote them with identical values; keep it exact)
         value = nq * rounds * steps / (total_ms / 1e3)
         kern_ms_avg = kern_ms / steps
+        unc_all = [int(stats.uncertified)]
+        if world > 1:  # queries re-run by the exact scan on EVERY rank (a rank with many re-runs paces the all-gather)
+            t = torch.zeros((world,), dtype=torch.int64, device=dev)
+            t[rank] = int(stats.uncertified)
+            dist.all_reduce(t)
+            unc_all = t.tolist()
 
         # ---- roofline of the dominant kernel (per launch, this rank's shard) -------------------------------------
         peaks = self.peaks
@@ -621,6 +627,20 @@ class Bench:
         roof["kernel_span"] = ("prepass + threshold selection + filter" if (mode == "kl" and stats.algo_used == 2)
                                else "one launch")
         roof["algorithmic_per_launch"] = {"flops": flops, "bytes": bytes_alg}
+        if mode == "kl" and stats.algo_used == 2:
+            # the many-queries KL filter is bound by looking at the keys, not by producing them: one FMNMX3 lane-op per two
+            # keys on 128 lanes per SM and clock is the floor of ONE sweep (the step is a 1/3 prepass + the real pass)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            clk_hz = (stats.filter_sm_mhz or 1900.0) * 1e6
+            floor_ms = float(nq) * n_local / (sms * 128.0 * clk_hz) * 1e3
+            roof["select_floor"] = {"ms_per_sweep": floor_ms, "sweeps_per_step": 1.0 + 1.0 / 3.0,
+                                    "frac": floor_ms * (1.0 + 1.0 / 3.0) / kern_ms_avg,
+                                    "note": "keys / (SMs x 128 lanes x in-kernel clock): the bound this kernel is measured against "
+                                            "(DESIGN.md section 4.2); the tensor fraction above counts 28 flop per pair"}
+        if mode == "kl" and stats.algo_used == 3:
+            roof["streamed_bytes_per_case"] = 64 if precision == "fp32" else 32
+            roof["note"] = ("achieved = 56 algorithmic bytes per case / kernel time; the kernel streams the 64-byte [hi|lo] bf16 row "
+                            "in certified precision and the 32-byte fp16 row in filter-only precision (same speed: DESIGN.md 4.3)")
 
         rec = {
             "value": value, "unit": "queries/s", "ms_per_step": total_ms / steps, "steps": steps,
@@ -628,7 +648,8 @@ class Bench:
             "config": workload_config(args, name, wl, n_total, k, precision, graph_note),
             "e2e": e2e, "gpu_launches": launches_per_step[0] * steps, "roofline": roof,
             "search_stats": {"algo_used": stats.algo_used, "parts": stats.parts, "kprime": stats.kprime,
-                             "uncertified": stats.uncertified, "kernel_launches_per_search": stats.kernel_launches,
+                             "uncertified": stats.uncertified, "uncertified_per_rank": unc_all,
+                             "kernel_launches_per_search": stats.kernel_launches,
                              "filter_sm_mhz": round(stats.filter_sm_mhz, 1)},
         }
         if clocks is not None:

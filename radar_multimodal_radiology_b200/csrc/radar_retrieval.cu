@@ -69,6 +69,7 @@ struct Plan {
     size_t off_cand, off_cnt, off_thr, off_gthr, off_sel, off_bound, off_qerr, off_apack, off_ucount, off_ulist;
     size_t off_groupmax;  // KL threshold prepass
     int groups, group_tiles, tile_stride, groups_per_slab;
+    size_t off_done;   // KL filter path: per-query "finished by kl_finish_kernel" flags
     int klf;           // KL mode: the dedicated many-queries kernel (kl_filter.cuh) runs the main pass
     int kl_fmt;        // its filter arithmetic (klf::kFmt*); also the KL stream path's table choice
     size_t off_fb_cand, off_fb_cnt, off_fb_sel;  // exact re-run of uncertified queries
@@ -78,6 +79,12 @@ struct Plan {
     size_t off_ks_zero, ks_zero_bytes, off_ks_pool, off_ks_best, off_ks_tilemax;
     int fb_parts;
     int64_t fb_rows_per_part;
+    // exact re-run, first wave: the first kRerunHead uncertified queries get their own launch with MANY corpus slabs (a
+    // handful of failed certificates must not be scanned by one CTA each: that is 4.5 ms for ONE query over 188 k rows and
+    // 0.2 s over 10 M); the rest -- if there ever are more -- go through the all-queries plan above
+    int fa_parts;
+    int64_t fa_rows_per_part;
+    size_t off_fa_cand, off_fa_cnt, off_fa_sel;
     size_t total;
 };
 
@@ -184,6 +191,27 @@ static void plan_parts_filter(int64_t q_tiles, int64_t n, int tile_rows, int uni
     *rows_per_part = tiles_per_part * tile_rows;
 }
 
+constexpr int64_t kRerunHead = 1024;
+
+// workspace of the exact re-run chain (both waves); `carve` is make_plan's allocator
+template <typename Carve>
+static void plan_rerun(Plan* pl, const radar_corpus_t* c, int64_t q, int k, int sms, Carve carve) {
+    const int64_t fa_q = q < kRerunHead ? q : kRerunHead;
+    const int64_t fa_tiles = ceil_div64(fa_q, kScanTQ);
+    plan_parts(fa_tiles, c->n, kScanTC, sms, 8, &pl->fa_parts, &pl->fa_rows_per_part);
+    pl->off_fa_cand = carve(sizeof(uint64_t) * fa_tiles * kScanTQ * pl->fa_parts * kCandCap);
+    pl->off_fa_cnt = carve(sizeof(uint32_t) * fa_tiles * kScanTQ * pl->fa_parts);
+    pl->off_fa_sel = carve(sizeof(uint64_t) * fa_q * k);
+    const int64_t fb_q = q > kRerunHead ? q - kRerunHead : 0;
+    if (fb_q > 0) {
+        const int64_t f_tiles = ceil_div64(fb_q, kScanTQ);
+        plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
+        pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
+        pl->off_fb_cnt = carve(sizeof(uint32_t) * f_tiles * kScanTQ * pl->fb_parts);
+        pl->off_fb_sel = carve(sizeof(uint64_t) * fb_q * k);
+    }
+}
+
 static bool kl_stream_supported(const radar_corpus_t* c, int64_t q, int mode, const DeviceInfo& di) {
     return di.major == 10 && mode == RADAR_MODE_KL && (c->klpack || c->kl16) && c->logq16 && q >= 1 && q <= kls::kMaxN &&
            c->n >= kls::kMinRows;
@@ -251,11 +279,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->off_ucount = pl->off_ks_zero + sizeof(uint32_t) * (5 * qp + 4);
         pl->off_ulist = carve(sizeof(uint32_t) * qp);
         pl->off_apack = carve(tc::apack_bytes(qp, RADAR_MODE_KL, c->d));
-        const int64_t f_tiles = ceil_div64(q, kScanTQ);
-        plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
-        pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
-        pl->off_fb_cnt = carve(sizeof(uint32_t) * f_tiles * kScanTQ * pl->fb_parts);
-        pl->off_fb_sel = carve(sizeof(uint64_t) * q * p->k);
+        plan_rerun(pl, c, q, p->k, sms, carve);
         pl->total = off;
         return RADAR_OK;
     }
@@ -305,6 +329,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
     pl->off_ulist = carve(sizeof(uint32_t) * q);
     if (algo == RADAR_ALGO_TC_FILTER) {
         pl->off_apack = carve(tc::apack_bytes(q_pad, p->mode, c->d));
+        if (pl->klf) pl->off_done = carve(static_cast<size_t>(q));
         // KL with many queries over a small corpus: the cold-start survivors (~k' ln n per query) cost more than a second
         // (partial) sweep of the cheap KL contraction, so a prepass over every tile_stride-th tile collects group maxima
         // and the real pass starts from near-exact thresholds (kl_filter.cuh).  About 256 groups per query (measured: 512 groups
@@ -335,12 +360,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         }
         if (p->precision == RADAR_PREC_FP32) {
             // exact re-run of uncertified queries: enqueued unconditionally with a device-side count, sized for all q
-            const int64_t fq = q;
-            const int64_t f_tiles = ceil_div64(fq, kScanTQ);
-            plan_parts(f_tiles, c->n, kScanTC, sms, 2, &pl->fb_parts, &pl->fb_rows_per_part);
-            pl->off_fb_cand = carve(sizeof(uint64_t) * f_tiles * kScanTQ * pl->fb_parts * kCandCap);
-            pl->off_fb_cnt = carve(sizeof(uint32_t) * f_tiles * kScanTQ * pl->fb_parts);
-            pl->off_fb_sel = carve(sizeof(uint64_t) * fq * p->k);
+            plan_rerun(pl, c, q, p->k, sms, carve);
         }
     }
     pl->total = off;
@@ -379,24 +399,48 @@ static int launch_scan(const ScanArgs& a, int64_t q_tiles, cudaStream_t st) {
 
 // Exact re-run (canonical CUDA-core scan) of the queries listed in ulist[0 .. *ucount): enqueued unconditionally, the
 // kernels read the count on the device and exit at once when it is zero -- no host round trip inside a search call.
-static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_t* queries, int mode, int k, float alpha,
-                              float oma, int64_t q_max, const uint32_t* ucount, const uint32_t* ulist, int fb_parts,
-                              int64_t fb_rows_per_part, uint64_t* fb_cand, uint32_t* fb_cnt, uint64_t* fb_sel,
-                              float* out_scores, int64_t* out_idx, uint64_t* out_packed, cudaStream_t st) {
+// One wave: queries ulist[skip .. skip + q_max) scanned with `parts` corpus slabs.
+static int launch_exact_rerun_wave(const radar_corpus_t* corpus, const radar_queries_t* queries, int mode, int k, float alpha,
+                                   float oma, int64_t q_max, uint32_t skip, const uint32_t* ucount, const uint32_t* ulist,
+                                   int parts, int64_t rows_per_part, uint64_t* cand, uint32_t* cnt, uint64_t* sel,
+                                   float* out_scores, int64_t* out_idx, uint64_t* out_packed, cudaStream_t st) {
     ScanArgs a{};
     a.q_emb = queries->emb_f32; a.p16 = queries->p16; a.entropy = queries->entropy;
-    a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist; a.nq_dev = ucount;
+    a.c_emb = corpus->emb_f32; a.logq16 = corpus->logq16; a.qmap = ulist + skip; a.nq_dev = ucount; a.nq_skip = skip;
     a.nq = q_max; a.n = corpus->n; a.d = corpus->d; a.mode = mode; a.alpha = alpha; a.oma = oma;
-    a.parts = fb_parts; a.rows_per_part = fb_rows_per_part; a.kp = k; a.cand = fb_cand; a.cnt = fb_cnt;
+    a.parts = parts; a.rows_per_part = rows_per_part; a.kp = k; a.cand = cand; a.cnt = cnt;
     int rc = launch_scan(a, ceil_div64(q_max, kScanTQ), st);
     if (rc) return rc;
     select_kernel<<<static_cast<unsigned>(ceil_div64(q_max, kSelWarps)), kSelWarps * 32, 0, st>>>(
-        fb_cand, fb_cnt, nullptr, q_max, ucount, fb_parts, kCandCap, k, fb_sel, nullptr);
+        cand, cnt, nullptr, q_max, ucount, parts, kCandCap, k, sel, nullptr, skip);
     RADAR_CUDA_CHECK(cudaGetLastError());
     FinalArgs g{};
-    g.sel = fb_sel; g.R = k; g.k = k; g.mode = mode; g.sort = 0; g.qmap = ulist; g.nq_dev = ucount;
+    g.sel = sel; g.R = k; g.k = k; g.mode = mode; g.sort = 0; g.qmap = ulist + skip; g.nq_dev = ucount; g.nq_skip = skip;
     g.idx_offset = corpus->idx_offset; g.out_scores = out_scores; g.out_idx = out_idx; g.out_packed = out_packed;
     RADAR_CUDA_CHECK(launch_final(g, q_max, st));
+    return RADAR_OK;
+}
+
+// Two waves (see Plan::fa_*): the first kRerunHead listed queries with many corpus slabs, the rest with the all-queries plan.
+static int launch_exact_rerun(const radar_corpus_t* corpus, const radar_queries_t* queries, int mode, int k, float alpha,
+                              float oma, int64_t q, const uint32_t* ucount, const uint32_t* ulist, const Plan& pl, uint8_t* ws,
+                              float* out_scores, int64_t* out_idx, uint64_t* out_packed, cudaStream_t st, int* launches) {
+    const int64_t fa_q = q < kRerunHead ? q : kRerunHead;
+    int rc = launch_exact_rerun_wave(corpus, queries, mode, k, alpha, oma, fa_q, 0u, ucount, ulist, pl.fa_parts,
+                                     pl.fa_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fa_cand),
+                                     reinterpret_cast<uint32_t*>(ws + pl.off_fa_cnt),
+                                     reinterpret_cast<uint64_t*>(ws + pl.off_fa_sel), out_scores, out_idx, out_packed, st);
+    if (rc) return rc;
+    *launches += 3;
+    if (q > kRerunHead) {
+        rc = launch_exact_rerun_wave(corpus, queries, mode, k, alpha, oma, q - kRerunHead, static_cast<uint32_t>(kRerunHead),
+                                     ucount, ulist, pl.fb_parts, pl.fb_rows_per_part,
+                                     reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
+                                     reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
+                                     reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, out_packed, st);
+        if (rc) return rc;
+        *launches += 3;
+    }
     return RADAR_OK;
 }
 
@@ -655,12 +699,9 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(cudaGetLastError());
         launches += 5;
         // queries whose pool overflowed or (fp32 mode) whose certificate failed are re-run by the exact scan
-        rc = launch_exact_rerun(corpus, queries, RADAR_MODE_KL, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
-                                pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
-                                reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
-                                reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, out_packed, st);
+        rc = launch_exact_rerun(corpus, queries, RADAR_MODE_KL, params->k, alpha, oma, q, ucount, ulist, pl, ws, out_scores,
+                                out_idx, out_packed, st, &launches);
         if (rc) return rc;
-        launches += 3;
         have_ucount = true;
     } else if (pl.algo == RADAR_ALGO_SIMT_EXACT) {
         ScanArgs a{};
@@ -716,21 +757,35 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
             clk_dev = fl.clk_dev;
         }
         launches += nl;
+        const uint8_t* done = nullptr;
+        if (pl.klf && pl.buf_parts <= 32 && params->k <= 64) {
+            // short candidate lists (the usual case after a prepass): gather + canonical re-score + rank + certificate in
+            // one warp-per-query kernel; queries with more than 64 candidates fall through to the generic kernels below
+            KlFinishArgs ka{};
+            ka.cand = cand; ka.cnt = cnt; ka.thr_final = thr; ka.p16 = queries->p16; ka.entropy = queries->entropy;
+            ka.logq16 = corpus->logq16; ka.qerr = certify ? qerr : nullptr; ka.nq = q; ka.parts = pl.buf_parts; ka.k = params->k;
+            ka.idx_offset = corpus->idx_offset; ka.out_scores = out_scores; ka.out_idx = out_idx; ka.out_packed = out_packed;
+            ka.uncert_count = ucount; ka.uncert_list = ulist; ka.done = ws + pl.off_done;
+            kl_finish_kernel<<<static_cast<unsigned>(ceil_div64(q, kFinishWarps)), kFinishWarps * 32, 0, st>>>(ka);
+            RADAR_CUDA_CHECK(cudaGetLastError());
+            ++launches;
+            done = ws + pl.off_done;
+        }
         select_kernel<<<static_cast<unsigned>(ceil_div64(q, kSelWarps)), kSelWarps * 32, 0, st>>>(
-            cand, cnt, thr, q, nullptr, pl.buf_parts, kCandCap, pl.R, sel, bound);
+            cand, cnt, thr, q, nullptr, pl.buf_parts, kCandCap, pl.R, sel, bound, 0u, done);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         RescoreArgs r{};
         r.q_emb = queries->emb_f32; r.p16 = queries->p16; r.entropy = queries->entropy;
         r.c_emb = corpus->emb_f32; r.logq16 = corpus->logq16; r.qmap = nullptr; r.nq = q; r.d = corpus->d;
-        r.mode = params->mode; r.alpha = alpha; r.oma = oma; r.R = pl.R; r.sel = sel;
+        r.mode = params->mode; r.alpha = alpha; r.oma = oma; r.R = pl.R; r.sel = sel; r.done = done;
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kRescoreSmemBytes)));
         rescore_kernel<<<static_cast<unsigned>(ceil_div64(q, kRsWarps)), kRsWarps * 32, kRescoreSmemBytes, st>>>(r);
         RADAR_CUDA_CHECK(cudaGetLastError());
         ++launches;
         FinalArgs f{};
-        f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 1; f.qmap = nullptr;
+        f.sel = sel; f.R = pl.R; f.k = params->k; f.mode = params->mode; f.sort = 1; f.qmap = nullptr; f.done = done;
         f.idx_offset = corpus->idx_offset; f.out_scores = out_scores; f.out_idx = out_idx; f.out_packed = out_packed;
         if (certify) {
             f.bound = bound; f.qerr = qerr; f.uncert_count = ucount; f.uncert_list = ulist;
@@ -738,13 +793,9 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         RADAR_CUDA_CHECK(launch_final(f, q, st));
         ++launches;
         if (certify) {
-            rc = launch_exact_rerun(corpus, queries, params->mode, params->k, alpha, oma, q, ucount, ulist, pl.fb_parts,
-                                    pl.fb_rows_per_part, reinterpret_cast<uint64_t*>(ws + pl.off_fb_cand),
-                                    reinterpret_cast<uint32_t*>(ws + pl.off_fb_cnt),
-                                    reinterpret_cast<uint64_t*>(ws + pl.off_fb_sel), out_scores, out_idx, out_packed,
-                                    st);
+            rc = launch_exact_rerun(corpus, queries, params->mode, params->k, alpha, oma, q, ucount, ulist, pl, ws,
+                                    out_scores, out_idx, out_packed, st, &launches);
             if (rc) return rc;
-            launches += 3;
             have_ucount = true;
         }
     }

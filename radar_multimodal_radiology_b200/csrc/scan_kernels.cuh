@@ -33,6 +33,7 @@ struct ScanArgs {
     const uint32_t* qmap;  // nullable: tile row -> query id (exact re-run of uncertified queries)
     const uint32_t* nq_dev;  // nullable: DEVICE-side number of tile rows in use (<= nq); lets the re-run of uncertified
                              // queries be enqueued without a host round trip -- CTAs beyond the count exit at once
+    uint32_t nq_skip;      // with nq_dev: the first nq_skip listed queries belong to another launch (count = *nq_dev - nq_skip)
     int64_t nq;            // tile rows in use (upper bound when nq_dev is set)
     int64_t n;             // corpus rows
     int d;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(kScanThreads) simt_scan_kernel(const ScanArgs 
     const int ty = tid >> 4, tx = tid & 15;
     const int part = blockIdx.y;
     const int64_t q0 = static_cast<int64_t>(blockIdx.x) * kScanTQ;
-    const int64_t nq = a.nq_dev ? min(static_cast<int64_t>(*a.nq_dev), a.nq) : a.nq;
+    const int64_t nq = a.nq_dev ? min(static_cast<int64_t>(*a.nq_dev > a.nq_skip ? *a.nq_dev - a.nq_skip : 0u), a.nq) : a.nq;
     if (q0 >= nq) return;
     const int64_t part_begin = static_cast<int64_t>(part) * a.rows_per_part;
     const int64_t part_end = min(a.n, part_begin + a.rows_per_part);
@@ -287,12 +288,14 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* 
                                                                 const float* __restrict__ thr_final, int64_t nq,
                                                                 const uint32_t* __restrict__ nq_dev, int parts, int cap,
                                                                 int R, uint64_t* __restrict__ sel,
-                                                                float* __restrict__ bound) {
+                                                                float* __restrict__ bound, uint32_t nq_skip = 0,
+                                                                const uint8_t* __restrict__ done = nullptr) {
     __shared__ uint64_t work[kSelWarps][kCandCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qi = static_cast<int64_t>(blockIdx.x) * kSelWarps + warp;
-    if (nq_dev) nq = min(nq, static_cast<int64_t>(*nq_dev));
+    if (nq_dev) nq = min(nq, static_cast<int64_t>(*nq_dev > nq_skip ? *nq_dev - nq_skip : 0u));
     if (qi >= nq) return;  // warp-uniform
+    if (done && done[qi]) return;  // finished by the fused KL kernel (kl_finish_kernel)
     uint64_t* w = work[warp];
     float b = -CUDART_INF_F;
     if (thr_final) {
@@ -350,6 +353,7 @@ struct RescoreArgs {
     float alpha, oma;
     int R;
     uint64_t* sel;
+    const uint8_t* done;  // nullable: queries already finished by kl_finish_kernel
 };
 
 // One warp per query, lanes = candidates.  The embedding rows of the (up to) 32 candidates of a group are fetched
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(const RescoreArg
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qi = static_cast<int64_t>(blockIdx.x) * kRsWarps + warp;
     if (qi >= a.nq) return;  // warp-uniform
+    if (a.done && a.done[qi]) return;
     float* tile = rs_smem + warp * (32 * kRsLd + kRsChunk);
     float* qrow = tile + 32 * kRsLd;
     const int64_t qid = a.qmap ? a.qmap[qi] : qi;
@@ -436,6 +441,7 @@ struct FinalArgs {
     int sort;  // 0: sel rows are already in final order
     const uint32_t* qmap;
     const uint32_t* nq_dev;  // nullable: device-side number of queries (CTAs beyond it exit)
+    uint32_t nq_skip;        // with nq_dev: count = *nq_dev - nq_skip (the first nq_skip listed queries belong to another launch)
     int64_t idx_offset;
     float* out_scores;
     int64_t* out_idx;
@@ -445,6 +451,7 @@ struct FinalArgs {
     const float* qerr;
     uint32_t* uncert_count;
     uint32_t* uncert_list;
+    const uint8_t* done;  // nullable: queries already finished by kl_finish_kernel
 };
 
 constexpr int kFinalThreads = 128;
@@ -454,7 +461,8 @@ __global__ void __launch_bounds__(kFinalThreads) final_kernel(const FinalArgs a)
     __shared__ uint64_t s[kFinalCap];
     const int64_t qi = blockIdx.x;
     const int tid = threadIdx.x;
-    if (a.nq_dev && qi >= static_cast<int64_t>(*a.nq_dev)) return;
+    if (a.nq_dev && qi >= static_cast<int64_t>(*a.nq_dev > a.nq_skip ? *a.nq_dev - a.nq_skip : 0u)) return;
+    if (a.done && a.done[qi]) return;
     const int P = max(next_pow2(a.R), 2);
     for (int i = tid; i < P; i += kFinalThreads) s[i] = i < a.R ? a.sel[qi * a.R + i] : 0ull;
     if (a.sort) bitonic_sort_desc(s, P, tid, kFinalThreads, [] { __syncthreads(); });
@@ -496,8 +504,9 @@ constexpr int kFinalWarps = 8;
 __global__ void __launch_bounds__(kFinalWarps * 32) final_warp_kernel(const FinalArgs a, int64_t nq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qi = static_cast<int64_t>(blockIdx.x) * kFinalWarps + warp;
-    if (a.nq_dev) nq = min(nq, static_cast<int64_t>(*a.nq_dev));
+    if (a.nq_dev) nq = min(nq, static_cast<int64_t>(*a.nq_dev > a.nq_skip ? *a.nq_dev - a.nq_skip : 0u));
     if (qi >= nq) return;  // warp-uniform
+    if (a.done && a.done[qi]) return;
     const uint64_t c = lane < a.R ? a.sel[qi * a.R + lane] : 0ull;
     int rank = 0;
 #pragma unroll
@@ -529,6 +538,131 @@ __global__ void __launch_bounds__(kFinalWarps * 32) final_warp_kernel(const Fina
             a.uncert_list[slot] = static_cast<uint32_t>(qid);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// KL filter path, short candidate lists: select + rescore + final in ONE kernel, one warp per query.  After a prepass the
+// buffers of a query hold a few dozen candidates in total; when they are at most 64 (two per lane) the warp gathers them
+// all, computes their canonical keys (every candidate, not only the best R by filter key: nothing is dropped here, so the
+// bound is just the largest final threshold), ranks them by counting, writes the top k and checks the certificate.
+// Queries with more candidates are left to the three generic kernels (done[qi] = 0).
+// ---------------------------------------------------------------------------------------------------
+struct KlFinishArgs {
+    const uint64_t* cand;     // [q][parts][kCandCap]
+    const uint32_t* cnt;      // [q][parts]
+    const float* thr_final;   // [q][parts]
+    const float* p16;
+    const float* entropy;
+    const float* logq16;
+    const float* qerr;        // nullable: no certificate (filter-only precision)
+    int64_t nq;
+    int parts, k;
+    int64_t idx_offset;
+    float* out_scores;
+    int64_t* out_idx;
+    uint64_t* out_packed;     // nullable
+    uint32_t* uncert_count;
+    uint32_t* uncert_list;
+    uint8_t* done;            // [q] out
+};
+
+constexpr int kFinishWarps = 8;
+
+__global__ void __launch_bounds__(kFinishWarps * 32) kl_finish_kernel(const KlFinishArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t qi = static_cast<int64_t>(blockIdx.x) * kFinishWarps + warp;
+    if (qi >= a.nq) return;  // warp-uniform
+    // counts and final thresholds of up to 32 buffers per round (parts is a few units)
+    int total = 0;
+    float b = -CUDART_INF_F;
+    for (int p0 = 0; p0 < a.parts; p0 += 32) {
+        const int p = p0 + lane;
+        const int c = p < a.parts ? static_cast<int>(a.cnt[qi * a.parts + p]) : 0;
+        if (p < a.parts) b = fmaxf(b, a.thr_final[qi * a.parts + p]);
+        total += __reduce_add_sync(0xffffffffu, c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if (total > 64 || a.parts > 32) {  // warp-uniform: the generic kernels take this query
+        if (lane == 0) a.done[qi] = 0;
+        return;
+    }
+    const int my_cnt = lane < a.parts ? static_cast<int>(a.cnt[qi * a.parts + lane]) : 0;
+    // gather: entry j of the concatenated buffers -> (buffer, offset)
+    uint64_t c[2] = {0ull, 0ull};
+    {
+        int base = 0;
+        for (int p = 0; p < a.parts; ++p) {
+            const int cp = __shfl_sync(0xffffffffu, my_cnt, p);
+            const uint64_t* src = a.cand + (qi * a.parts + p) * kCandCap;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int j = lane + 32 * e;
+                if (j >= base && j < base + cp) c[e] = src[j - base];
+            }
+            base += cp;
+        }
+    }
+    // canonical keys (the fma chain of oracle/radar_oracle.c: index order, fp32)
+    const float h = a.entropy[qi];
+    const float pv = lane < kObsPad ? a.p16[qi * kObsPad + lane] : 0.0f;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const uint32_t row = composite_row(c[e]);
+        const bool live = c[e] != 0ull;
+        float lv[16];
+        if (live) {
+            const float4* ll = reinterpret_cast<const float4*>(a.logq16 + static_cast<int64_t>(row) * kObsPad);
+            const float4 l0 = __ldg(ll), l1 = __ldg(ll + 1), l2 = __ldg(ll + 2), l3 = __ldg(ll + 3);
+            lv[0] = l0.x; lv[1] = l0.y; lv[2] = l0.z; lv[3] = l0.w; lv[4] = l1.x; lv[5] = l1.y; lv[6] = l1.z; lv[7] = l1.w;
+            lv[8] = l2.x; lv[9] = l2.y; lv[10] = l2.z; lv[11] = l2.w; lv[12] = l3.x; lv[13] = l3.y; lv[14] = l3.z; lv[15] = l3.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lv[j] = 0.0f;
+        }
+        float x = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kNumObs; ++j) x = __fmaf_rn(__shfl_sync(0xffffffffu, pv, j), lv[j], x);
+        if (live) c[e] = make_composite(__fsub_rn(x, h), row);
+    }
+    // rank by counting (composites are distinct; empty slots rank behind everything, by position)
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+        for (int j = 0; j < 32; ++j) {
+            const uint64_t o = __shfl_sync(0xffffffffu, c[f], j);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int pos_o = j + 32 * f, pos_me = lane + 32 * e;
+                rank[e] += (o > c[e] || (o == c[e] && pos_o < pos_me)) ? 1 : 0;
+            }
+        }
+    }
+    bool cert_ok = true;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (rank[e] < a.k) {
+            float sc;
+            int64_t id;
+            if (c[e] != 0ull) {
+                sc = api_score_from_key(RADAR_MODE_KL, composite_key(c[e]));
+                id = static_cast<int64_t>(composite_row(c[e])) + a.idx_offset;
+            } else {
+                sc = CUDART_INF_F;
+                id = -1;
+            }
+            a.out_scores[qi * a.k + rank[e]] = sc;
+            a.out_idx[qi * a.k + rank[e]] = id;
+            if (a.out_packed) a.out_packed[qi * a.k + rank[e]] = c[e] != 0ull ? packed_global(c[e], a.idx_offset) : 0ull;
+        }
+        if (a.qerr && rank[e] == a.k - 1 && b > -CUDART_INF_F)  // exactly one slot holds the k-th best entry
+            cert_ok = (c[e] != 0ull) && (b + a.qerr[qi] < composite_key(c[e]));
+    }
+    if (!cert_ok) {
+        const uint32_t slot = atomicAdd(a.uncert_count, 1u);
+        a.uncert_list[slot] = static_cast<uint32_t>(qi);
+    }
+    if (lane == 0) a.done[qi] = 1;
 }
 
 static inline cudaError_t launch_final(const FinalArgs& a, int64_t nq, cudaStream_t st) {

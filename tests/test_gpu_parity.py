@@ -250,6 +250,26 @@ def test_tc_fp32_mode_is_certified_bit_identical(dev, mode, k):
 
 
 @pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
+def test_exact_rerun_waves_when_most_certificates_fail(dev, mode):
+    """k' = k leaves no gap between the k-th canonical key and the filter's bound, so in fp32 precision nearly every
+    certificate fails: the exact re-run takes its first 1 024 queries through the many-slab wave and the rest through the
+    all-queries wave -- and the result is still the oracle's, bit for bit.  (One failed certificate used to be scanned by a
+    single CTA: 4.5 ms for one query over 188 k rows.)"""
+    p = make_problem(20000, 2500, d=64, seed=58)
+    idx = _index(p, dev, precision="fp32", algo="tc", overfetch=10)
+    s, i = _search(idx, p, mode, 10)
+    ws, wi = _oracle(p, mode, 10)
+    assert idx.last_stats.algo_used == 2
+    if mode != "kl":  # (the KL path re-scores EVERY candidate above its prepass threshold, so even k' = k mostly certifies)
+        assert idx.last_stats.uncertified > 1024, idx.last_stats
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+    # a handful of failures (the usual case): first wave only
+    idx2 = _index(p, dev, precision="fp32", algo="tc", overfetch=14)
+    s, i = _search(idx2, p, mode, 10)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws), idx2.last_stats
+
+
+@pytest.mark.parametrize("mode", ["dpr", "kl", "hybrid"])
 @pytest.mark.parametrize("k", [10, 32])
 def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
     """bf16 tolerance statement: ids have recall@k >= 0.999 against the fp32 result; every returned score is
