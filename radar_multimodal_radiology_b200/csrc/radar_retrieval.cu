@@ -358,6 +358,29 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
                 pl->off_groupmax = carve(sizeof(uint32_t) * q_pad * groups);
             }
         }
+        // DPR / hybrid over a SHORT sweep (shard of at most 2 M rows): sampled threshold prepass of the general filter
+        // (tc_filter.cuh: launch_filter).  One tile in RADAR_TC_PREPASS_STRIDE, ~256 groups per query.
+        if (!pl->klf && c->n <= (2ll << 20) && c->n >= (1ll << 17) && pl->kp <= 64) {
+#ifndef RADAR_TC_PREPASS_STRIDE
+#define RADAR_TC_PREPASS_STRIDE 16
+#endif
+            const int64_t stride = RADAR_TC_PREPASS_STRIDE;
+            const int bn = tc::block_n_for_mode(p->mode);
+            const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, bn), stride);
+            int64_t tgs = 256 / pl->parts;
+            if (tgs > slab_tiles) tgs = slab_tiles;
+            if (tgs < 1) tgs = 1;
+            const int64_t gt = ceil_div64(slab_tiles, tgs);
+            tgs = ceil_div64(slab_tiles, gt);
+            const int64_t groups = tgs * pl->parts;
+            if (stride > 1 && groups >= 2 * pl->kp && groups <= 32 * tc::kMaxGroups32) {
+                pl->groups = static_cast<int>(groups);
+                pl->group_tiles = static_cast<int>(gt);
+                pl->tile_stride = static_cast<int>(stride);
+                pl->groups_per_slab = static_cast<int>(tgs);
+                pl->off_groupmax = carve(sizeof(uint32_t) * q_pad * groups);
+            }
+        }
         if (p->precision == RADAR_PREC_FP32) {
             // exact re-run of uncertified queries: enqueued unconditionally with a device-side count, sized for all q
             plan_rerun(pl, c, q, p->k, sms, carve);

@@ -1099,6 +1099,35 @@ static inline void fill_col_max(const radar_corpus_t* c, float* out) {
     for (int j = 0; j < kObsPad; ++j) out[j] = given ? c->logq_col_max[j] * 1.0001f : c->logq_max_abs;
 }
 
+// k'-th largest group maximum per query (one warp per query, up to 512 groups in registers, bit-wise radix descent) ->
+// initial threshold of the real pass
+constexpr int kMaxGroups32 = 16;
+__global__ void __launch_bounds__(256) group_threshold_kernel(const uint32_t* __restrict__ groupmax, int64_t q, int groups,
+                                                              int kp, uint32_t* __restrict__ gthr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t qi = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (qi >= q) return;
+    const uint32_t* src = groupmax + qi * groups;
+    uint32_t val[kMaxGroups32];
+#pragma unroll
+    for (int e = 0; e < kMaxGroups32; ++e) {
+        const int i = lane + 32 * e;
+        val[e] = i < groups ? src[i] : 0u;
+    }
+    uint32_t key = 0;
+    if (groups >= kp) {
+#pragma unroll 1
+        for (int b = 31; b >= 0; --b) {
+            const uint32_t trial = key | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < kMaxGroups32; ++e) c += val[e] >= trial ? 1 : 0;
+            if (__reduce_add_sync(0xffffffffu, c) >= kp) key = trial;
+        }
+    }
+    if (lane == 0) gthr[qi] = key;  // 0 = no threshold
+}
+
 // apack region layout: [q_pad * a_cols] uint16, then (256-byte aligned) qshift [q_pad] floats
 static inline size_t apack_bytes(int64_t q_pad, int mode, int d) {
     size_t b = sizeof(uint16_t) * static_cast<size_t>(q_pad) * a_cols_for(mode, d);
@@ -1156,6 +1185,36 @@ static int launch_filter(FilterLaunch& fl, cudaStream_t st, int* launches) {
         return RADAR_E_ARG;
     }
 #endif
+    auto launch_mode = [&](FilterLaunch& l, const FilterArgs& args) {
+        if (l.mode == RADAR_MODE_DPR)
+            return d512 ? launch_filter_mode<RADAR_MODE_DPR, 8>(l, args, st) : launch_filter_mode<RADAR_MODE_DPR, 0>(l, args, st);
+        return d512 ? launch_filter_mode<RADAR_MODE_HYBRID, 8>(l, args, st) : launch_filter_mode<RADAR_MODE_HYBRID, 0>(l, args, st);
+    };
+    if (fl.groups > 0 && fl.dbg_scores == nullptr) {
+        // SHORT SWEEPS (a few hundred thousand rows per query tile: config 3, shards of an 8-GPU run): the cold start of the
+        // running thresholds -- ~k' ln(n / k') survivors per query through the rare path -- is no longer hidden behind the
+        // MMAs.  A prepass of the same kernel over every tile_stride-th tile only records per query the maximum key of every
+        // group of sampled tiles (no rare path at all); the k'-th largest group maximum is a valid initial threshold, and the
+        // real pass sees ~k' ln(tile_stride) survivors instead.
+        RADAR_CUDA_CHECK(cudaMemsetAsync(fl.groupmax, 0, sizeof(uint32_t) * static_cast<size_t>(q_pad) * fl.groups, st));
+        FilterArgs fp = fa;
+        fp.prepass = 1; fp.groupmax = fl.groupmax; fp.groups = fl.groups; fp.group_tiles = fl.group_tiles;
+        fp.tile_stride = fl.tile_stride; fp.groups_per_slab = fl.groups_per_slab;
+        // the profiled span covers the prepass, the threshold selection and the real pass
+        cudaEvent_t e1 = fl.ev_stop;
+        fl.ev_stop = nullptr;
+        rc = launch_mode(fl, fp);
+        fl.ev_start = nullptr;
+        fl.ev_stop = e1;
+        if (rc) return rc;
+        group_threshold_kernel<<<static_cast<unsigned>((fl.q * 32 + 255) / 256), 256, 0, st>>>(fl.groupmax, fl.q, fl.groups,
+                                                                                                 fl.kp, fl.gthr);
+        RADAR_CUDA_CHECK(cudaGetLastError());
+        // the progress words of the window protocol must start from zero again
+        RADAR_CUDA_CHECK(cudaMemsetAsync(fa.progress, 0, sizeof(unsigned long long) * kMaxUnits, st));
+        fa.gthr_init = 1;
+        *launches += 2;
+    }
     if (fl.mode == RADAR_MODE_DPR)
         rc = d512 ? launch_filter_mode<RADAR_MODE_DPR, 8>(fl, fa, st) : launch_filter_mode<RADAR_MODE_DPR, 0>(fl, fa, st);
     else

@@ -289,6 +289,25 @@ def test_tc_bf16_mode_recall_and_canonical_scores(dev, mode, k):
 
 
 @pytest.mark.parametrize("mode", ["dpr", "hybrid"])
+@pytest.mark.parametrize("k", [10, 32])
+def test_tc_filter_sampled_prepass_on_short_sweeps(dev, mode, k):
+    """131 072 ... 2 M rows per shard: the general filter first runs a sampled prepass (group maxima over every 16th tile ->
+    initial thresholds) and then the real pass; fp32 results stay bit-identical, bf16 recall holds, and the prepass really
+    ran (two extra launches)."""
+    p = make_problem(300001, 4800, d=64, seed=90 + k)
+    ws, wi = _oracle(p, mode, k)
+    idx = _index(p, dev, precision="fp32", algo="tc")
+    s, i = _search(idx, p, mode, k)
+    st = idx.last_stats
+    assert st.algo_used == 2 and np.array_equal(i, wi) and np.array_equal(s, ws)
+    # pack, [prepass, thresholds], filter, select, rescore, final, 2 waves x 3 kernels of the exact re-run chain
+    # (k = 32 keeps k' = 96 candidates: above the prepass limit of 64, so that shape runs without it)
+    assert st.kernel_launches == (13 if k == 10 else 11), st
+    s, i = _search(idx, p, mode, k, precision="bf16")
+    assert np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)]) >= 0.999
+
+
+@pytest.mark.parametrize("mode", ["dpr", "hybrid"])
 def test_tc_filter_adversarial_row_order_stays_exact(dev, mode):
     """Corpus rows ordered so that EVERY query's score keeps rising along the sweep (running thresholds are stale for as
     long as possible, every tile has survivors, buffers compact again and again): the tcgen05 filter must still return
