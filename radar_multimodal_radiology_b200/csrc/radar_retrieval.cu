@@ -358,13 +358,21 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
                 pl->off_groupmax = carve(sizeof(uint32_t) * q_pad * groups);
             }
         }
-        // DPR / hybrid over a SHORT sweep (shard of at most 2 M rows): sampled threshold prepass of the general filter
-        // (tc_filter.cuh: launch_filter).  One tile in RADAR_TC_PREPASS_STRIDE, ~256 groups per query.
-        if (!pl->klf && c->n <= (2ll << 20) && c->n >= (1ll << 17) && pl->kp <= 64) {
+        // DPR / hybrid: sampled threshold prepass of the general filter (tc_filter.cuh: launch_filter) -- about 80 k sampled
+        // rows per query (one tile in 16 on a 1.25 M-row shard, one in 128 on 10 M rows), ~256 groups per query.
+        // On short sweeps the cold start of the thresholds is NOT hidden behind the MMAs (1.25 M-row shards of an 8-GPU
+        // run: 16.2 -> 15.3 ms per step; config 3: 21.0 -> 19.4 ms); on a 10 M-row sweep it is, and the 0.8 % of extra MMAs
+        // pays for itself (118.7 -> 117.9 ms).  RADAR_TC_PREPASS_MAX_ROWS can switch it off above a shard size.
+#ifndef RADAR_TC_PREPASS_MAX_ROWS
+#define RADAR_TC_PREPASS_MAX_ROWS (1ll << 40)
+#endif
+        if (!pl->klf && c->n <= RADAR_TC_PREPASS_MAX_ROWS && c->n >= (1ll << 17) && pl->kp <= 64) {
 #ifndef RADAR_TC_PREPASS_STRIDE
 #define RADAR_TC_PREPASS_STRIDE 16
 #endif
-            const int64_t stride = RADAR_TC_PREPASS_STRIDE;
+            int64_t stride = c->n / 78125;
+            if (stride < RADAR_TC_PREPASS_STRIDE) stride = RADAR_TC_PREPASS_STRIDE;
+            if (stride > 256) stride = 256;
             const int bn = tc::block_n_for_mode(p->mode);
             const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, bn), stride);
             int64_t tgs = 256 / pl->parts;
