@@ -366,7 +366,7 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
 #ifndef RADAR_TC_PREPASS_MAX_ROWS
 #define RADAR_TC_PREPASS_MAX_ROWS (1ll << 40)
 #endif
-        if (!pl->klf && c->n <= RADAR_TC_PREPASS_MAX_ROWS && c->n >= (1ll << 17) && pl->kp <= 64) {
+        if (!pl->klf && c->n <= RADAR_TC_PREPASS_MAX_ROWS && c->n >= (1ll << 17) && pl->kp <= 128) {
 #ifndef RADAR_TC_PREPASS_STRIDE
 #define RADAR_TC_PREPASS_STRIDE 16
 #endif
@@ -375,7 +375,10 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
             if (stride > 256) stride = 256;
             const int bn = tc::block_n_for_mode(p->mode);
             const int64_t slab_tiles = ceil_div64(ceil_div64(pl->rows_per_part, bn), stride);
-            int64_t tgs = 256 / pl->parts;
+            // ~256 groups per query, 4 k' of them when many candidates are kept (k' = 96 for top-32), at most what the threshold kernel holds
+            int64_t want = 4ll * pl->kp > 256 ? 4ll * pl->kp : 256;
+            if (want > 32 * tc::kMaxGroups32) want = 32 * tc::kMaxGroups32;
+            int64_t tgs = want / pl->parts;
             if (tgs > slab_tiles) tgs = slab_tiles;
             if (tgs < 1) tgs = 1;
             const int64_t gt = ceil_div64(slab_tiles, tgs);

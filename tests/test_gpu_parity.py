@@ -301,10 +301,24 @@ def test_tc_filter_sampled_prepass_on_short_sweeps(dev, mode, k):
     st = idx.last_stats
     assert st.algo_used == 2 and np.array_equal(i, wi) and np.array_equal(s, ws)
     # pack, [prepass, thresholds], filter, select, rescore, final, 2 waves x 3 kernels of the exact re-run chain
-    # (k = 32 keeps k' = 96 candidates: above the prepass limit of 64, so that shape runs without it)
+    # (k = 32 keeps k' = 96 candidates: 300 001 rows sampled every 16th tile give fewer than 2 k' groups, so that shape
+    # runs without the prepass; test_tc_filter_prepass_with_many_candidates covers k = 32 with it)
     assert st.kernel_launches == (13 if k == 10 else 11), st
     s, i = _search(idx, p, mode, k, precision="bf16")
     assert np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)]) >= 0.999
+
+
+def test_tc_filter_prepass_with_many_candidates(dev):
+    """top-32 (k' = 96 candidates per query) over a 1.3 M-row shard: the sampled prepass runs with ~4 k' groups and the
+    fp32 result stays bit-identical to the oracle."""
+    p = make_problem(1300003, 512, d=64, seed=77)
+    ws, wi = _oracle(p, "hybrid", 32)
+    idx = _index(p, dev, precision="fp32", algo="tc")
+    s, i = _search(idx, p, "hybrid", 32)
+    st = idx.last_stats
+    # pack, prepass, thresholds, filter, select, rescore, final + one wave of the exact re-run chain (<= 1 024 queries)
+    assert st.algo_used == 2 and st.kernel_launches == 10, st
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
 
 
 @pytest.mark.parametrize("mode", ["dpr", "hybrid"])
