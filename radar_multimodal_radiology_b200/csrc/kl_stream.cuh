@@ -5,9 +5,9 @@
 // candidate buffer per corpus slab; with a handful of queries that leaves 7 of 8 epilogue warps idle and lets every
 // slab warm its thresholds up on its own.  Here the roles are swapped and the candidates are pooled:
 //
-//   boot    (CUDA cores)   canonical keys of a strided SAMPLE of 256-row tiles; per query the maximum of every
-//                          sample tile.  The k'-th largest tile maximum is a valid lower bound of the k'-th best key
-//                          of the whole corpus (tile maxima are distinct cases) -> initial thresholds.
+//   boot    (tcgen05)      the stream kernel's BOOT instantiation over a strided SAMPLE of super-tiles: per query the maximum
+//                          filter key of every sampled super-tile.  The k'-th largest tile maximum is a valid lower bound of
+//                          the k'-th best filter key of the whole corpus (tile maxima are distinct cases) -> initial thresholds.
 //   stream  (tcgen05)      CTA pairs sweep the corpus once.  A operand = 256 corpus rows of the bf16 [hi|lo] log table
 //                          (TMA -> smem ring), B operand = the packed queries (resident in smem), D = [256 cases x N
 //                          queries] fp32 in TMEM, 512/N accumulator stages.  Epilogue thread = one case: it compares
@@ -62,112 +62,53 @@ constexpr int kStreamThreads = 384;     // warp 0 TMA, warps 1 / 11 MMA, warps 2
 #define RADAR_KLS_RELOAD 4
 #endif
 #ifndef RADAR_KLS_MAX_SAMPLE
-#define RADAR_KLS_MAX_SAMPLE 1024
+#define RADAR_KLS_MAX_SAMPLE 2048
 #endif
 constexpr int kRefreshEvery = RADAR_KLS_REFRESH_EVERY;  // appends of a query between threshold refresh attempts
 constexpr int kThrReload = RADAR_KLS_RELOAD;            // super-tiles between reloads of the published thresholds
 constexpr int kMinRows = 1 << 16;       // smaller corpora use the general path
 constexpr int kBootThreads = 256;
-constexpr int kBootRows = 256;          // rows of one sample tile
 constexpr int kMaxSample = RADAR_KLS_MAX_SAMPLE;  // sample tiles of the boot pass (k'-th largest tile maximum = first threshold)
 
 __host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one query's pooled buffer
     int c = (1 << 20) / n_pad;
     return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
 }
-inline int sample_tiles_for(int n_pad, int64_t boot_tiles) {
-    int64_t s = (32ll * kMaxSample) / n_pad;
-    if (s < 256) s = 256;
-    if (s > kMaxSample) s = kMaxSample;
-    return static_cast<int>(s < boot_tiles ? s : boot_tiles);
+inline int sample_tiles_for(int n_pad, int64_t tiles) {  // sampled super-tiles of the boot pass
+    (void)n_pad;
+    return static_cast<int>(kMaxSample < tiles ? kMaxSample : tiles);
 }
 
-// ---- boot: tile maxima of the canonical KL key over a strided sample of 256-row tiles -----------------------------
+// ---- boot threshold: k'-th largest sampled super-tile maximum per query -------------------------------------------
+// The maxima come from the BOOT instantiation of the stream kernel (filter keys of a strided sample of super-tiles): the
+// k'-th largest is a valid lower bound of the k'-th best filter key of the whole corpus (tile maxima are distinct cases).
 struct BootArgs {
-    const float* logq16;   // [n][16]
-    const float* p16;      // [q][16]
-    const float* entropy;  // [q]
-    const float* qerr;     // [q]
-    int64_t n, boot_tiles; // corpus rows, 256-row tiles
-    int q, sample_tiles, kp;
-    uint32_t* tilemax;     // [q][sample_tiles] ord-encoded keys (0 = no valid row)
-    uint32_t* gthr;        // [q] out
+    const uint32_t* tilemax;  // [q][sample_tiles] ord-encoded filter keys (0 = no valid row)
+    int sample_tiles, kp;
+    uint32_t* gthr;           // [q] out
 };
 
-__global__ void __launch_bounds__(kBootThreads) kl_boot_kernel(const BootArgs a) {
-    __shared__ __align__(16) float ps[kMaxN * kObsPad];
-    __shared__ float hs[kMaxN];
-    __shared__ uint32_t wmax[kBootThreads / 32][kMaxN];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q4 = (a.q + 3) & ~3;
-    for (int i = tid; i < q4 * kObsPad; i += kBootThreads) ps[i] = i < a.q * kObsPad ? a.p16[i] : 0.0f;
-    for (int i = tid; i < q4; i += kBootThreads) hs[i] = i < a.q ? a.entropy[i] : 0.0f;
-    __syncthreads();
-    for (int s = blockIdx.x; s < a.sample_tiles; s += gridDim.x) {
-        const int64_t tile = static_cast<int64_t>(s) * a.boot_tiles / a.sample_tiles;  // strided over the whole corpus
-        const int64_t row = tile * kBootRows + tid;
-        const bool valid = row < a.n;
-        float l[kObsPad];
-        {
-            const float4* src = reinterpret_cast<const float4*>(a.logq16 + (valid ? row : 0) * kObsPad);
-            const float4 l0 = __ldg(src), l1 = __ldg(src + 1), l2 = __ldg(src + 2), l3 = __ldg(src + 3);
-            l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
-            l[8] = l2.x; l[9] = l2.y; l[10] = l2.z; l[11] = l2.w; l[12] = l3.x; l[13] = l3.y; l[14] = l3.z; l[15] = l3.w;
-        }
-        for (int qi = 0; qi < q4; qi += 4) {  // four independent canonical chains per step
-            float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                float4 pv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pv[u] = *reinterpret_cast<const float4*>(ps + (qi + u) * kObsPad + 4 * j4);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    x[u] = __fmaf_rn(pv[u].x, l[4 * j4 + 0], x[u]);
-                    x[u] = __fmaf_rn(pv[u].y, l[4 * j4 + 1], x[u]);
-                    if (j4 < 3) {  // observations 14 and 15 are padding
-                        x[u] = __fmaf_rn(pv[u].z, l[4 * j4 + 2], x[u]);
-                        x[u] = __fmaf_rn(pv[u].w, l[4 * j4 + 3], x[u]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t o = valid ? f2ord(__fsub_rn(x[u], hs[qi + u])) : 0u;
-                const uint32_t m = __reduce_max_sync(0xffffffffu, o);
-                if (lane == 0) wmax[warp][qi + u] = m;
-            }
-        }
-        __syncthreads();
-        for (int qi = tid; qi < a.q; qi += kBootThreads) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int w = 0; w < kBootThreads / 32; ++w) m = max(m, wmax[w][qi]);
-            a.tilemax[static_cast<int64_t>(qi) * a.sample_tiles + s] = m;
-        }
-        __syncthreads();
-    }
-}
-
-// k'-th largest tile maximum per query (one warp = one CTA per query, values in registers) -> initial threshold,
-// lowered by the filter error bound
-__global__ void __launch_bounds__(32) kl_boot_threshold_kernel(const BootArgs a) {
-    const int qi = blockIdx.x, lane = threadIdx.x;
+// one CTA per query, values in registers, radix descent two bits per step (three independent counts, one block-wide sum)
+__global__ void __launch_bounds__(kBootThreads) kl_boot_threshold_kernel(const BootArgs a) {
+    static_assert(kMaxSample % kBootThreads == 0, "sample tiles per thread");
+    __shared__ int cnt[2][3][kBootThreads / 32];
+    const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t* src = a.tilemax + static_cast<int64_t>(qi) * a.sample_tiles;
-    uint32_t val[kMaxSample / 32];
+    uint32_t val[kMaxSample / kBootThreads];
 #pragma unroll
-    for (int e = 0; e < kMaxSample / 32; ++e) {
-        const int i = lane + 32 * e;
+    for (int e = 0; e < kMaxSample / kBootThreads; ++e) {
+        const int i = tid + kBootThreads * e;
         val[e] = i < a.sample_tiles ? src[i] : 0u;
     }
     uint32_t key = 0;
     if (a.sample_tiles >= a.kp) {
+        int buf = 0;
 #pragma unroll 1
-        for (int b = 30; b >= 0; b -= 2) {  // two bits per step: three independent counts, one dependent decision
+        for (int b = 30; b >= 0; b -= 2, buf ^= 1) {
             const uint32_t t1 = key | (1u << b), t2 = key | (2u << b), t3 = key | (3u << b);
             int c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-            for (int e = 0; e < kMaxSample / 32; ++e) {
+            for (int e = 0; e < kMaxSample / kBootThreads; ++e) {
                 c1 += val[e] >= t1 ? 1 : 0;
                 c2 += val[e] >= t2 ? 1 : 0;
                 c3 += val[e] >= t3 ? 1 : 0;
@@ -175,10 +116,23 @@ __global__ void __launch_bounds__(32) kl_boot_threshold_kernel(const BootArgs a)
             c1 = __reduce_add_sync(0xffffffffu, c1);
             c2 = __reduce_add_sync(0xffffffffu, c2);
             c3 = __reduce_add_sync(0xffffffffu, c3);
+            if (lane == 0) {
+                cnt[buf][0][warp] = c1;
+                cnt[buf][1][warp] = c2;
+                cnt[buf][2][warp] = c3;
+            }
+            __syncthreads();  // the other buffer is rewritten only after the next barrier: one barrier per step is enough
+            c1 = c2 = c3 = 0;
+#pragma unroll
+            for (int w = 0; w < kBootThreads / 32; ++w) {
+                c1 += cnt[buf][0][w];
+                c2 += cnt[buf][1][w];
+                c3 += cnt[buf][2][w];
+            }
             key = c3 >= a.kp ? t3 : (c2 >= a.kp ? t2 : (c1 >= a.kp ? t1 : key));
         }
     }
-    if (lane == 0) a.gthr[qi] = key != 0u ? f2ord(__fsub_rn(ord2f(key), a.qerr[qi])) : 0u;  // 0 = no threshold
+    if (tid == 0) a.gthr[qi] = key;  // 0 = no threshold
 }
 
 // ---- stream -------------------------------------------------------------------------------------------------
@@ -195,6 +149,9 @@ struct StreamArgs {
     uint64_t* best;              // [n_pad][kCandCap] running best-k' list of every query (touched under the lock only)
     uint64_t* pool;              // [n_pad][pool_cap]
     int reload;                  // super-tiles (of one epilogue set) between reloads of the published thresholds
+    // BOOT instantiation only: `tiles` counts the SAMPLED super-tiles (sample s = super-tile s * total_tiles / tiles)
+    int64_t total_tiles;
+    uint32_t* tilemax;           // [q][tiles] ord-encoded maximum filter key of every sampled super-tile (zeroed by the caller)
 };
 
 constexpr size_t kStreamSmemBytes = 1024 + static_cast<size_t>(kSlots) * slot_bytes(kFmtBf16x3) + 128 * 64 /*queries*/ +
@@ -217,6 +174,11 @@ __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ float redux_fmax(float v) {  // sm_100a: warp-wide float maximum in one instruction
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
 }
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
@@ -269,7 +231,9 @@ __device__ __noinline__ void refresh_threshold(const StreamArgs& a, int qi, uint
 
 // FMT (klf::kFmt*): bf16 hi/lo x 3 products on klpack (64 B rows), or fp16 x 1 / x 2 products on kl16 (32 B rows: half
 // the HBM bytes per case); the fp16 accumulators are scaled by 2^24 (kl_filter.cuh), thresholds are compared in scaled units
-template <int FMT>
+// BOOT: the same pipeline over a strided SAMPLE of super-tiles; the epilogue only reduces, per query, the maximum filter key of
+// every sampled super-tile (redux.sync.max.f32 over the 32 cases of a warp, one atomicMax per query and warp) -> tilemax.
+template <int FMT, bool BOOT>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_constant__ CUtensorMap map_q,
                  const StreamArgs a) {
@@ -343,8 +307,9 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             mbar_wait(&empty_bar[slot], sph ^ 1);
             if (elect_one()) {
                 if (leader) mbar_expect_tx(&full_bar[slot], kSlotBytes * 2);
+                const int64_t tt = BOOT ? t * a.total_tiles / a.tiles : t;
                 tma_load_2d_pair(&map_kl, smem_u32(&full_bar[slot]), smem_u32(ring + slot * kSlotBytes), 0,
-                                 static_cast<int>(t * kTileRows) + static_cast<int>(cta_rank) * 256);
+                                 static_cast<int>(tt * kTileRows) + static_cast<int>(cta_rank) * 256);
             }
             __syncwarp();
             if (++slot == kSlots) {
@@ -401,7 +366,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         // ================================ threshold refresher ================================
         // Folding pooled entries into a query's best-k' list takes microseconds; done by an epilogue warp it would hold
         // up the accumulator hand-off of the whole CTA pair, so the epilogue warps only raise a request bit.
-        while (true) {
+        while (!BOOT) {
             bool any = false;
             for (int w = 0; w < N / 32; ++w) {
                 uint32_t bits = 0;
@@ -437,7 +402,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         // thresholds in accumulator units: key + H
         uint32_t pending[kMaxN / 32];
 #pragma unroll
-        for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
+        for (int i = 0; i < kMaxN / 32; ++i) pending[i] = (!BOOT && i < nq32) ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
         auto commit_thresholds = [&]() {
 #pragma unroll
             for (int i = 0; i < kMaxN / 32; ++i) {
@@ -497,7 +462,7 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             }
             __syncwarp();
         };
-        commit_thresholds();
+        if (!BOOT) commit_thresholds();
         // A waiter must see every phase of its barriers: with an even number of stage pairs (a power of two) a set meets
         // each of "its" stage pairs on every use; with a single stage pair (N = 256) set 0 takes every super-tile.
         const uint32_t jstep = spairs > 1 ? 2u : 1u;
@@ -508,13 +473,13 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
             const int64_t t = unit + static_cast<int64_t>(j) * units;
             if (t >= a.tiles) break;
             const uint32_t sp = j & sp_mask, aph = (j >> sp_shift) & 1u;
-            if (++since == static_cast<uint32_t>(a.reload)) {  // use the values requested a few super-tiles ago, request fresh ones
+            if (!BOOT && ++since == static_cast<uint32_t>(a.reload)) {  // use the values requested a few super-tiles ago, request fresh ones
                 since = 0;
                 commit_thresholds();
 #pragma unroll
                 for (int i = 0; i < kMaxN / 32; ++i) pending[i] = i < nq32 ? ld_relaxed_u32(a.gthr + lane + 32 * i) : 0u;
             }
-            const int64_t row0 = t * kTileRows + static_cast<int64_t>(cta_rank) * 256 + quad * 32 + lane;
+            const int64_t row0 = (BOOT ? t * a.total_tiles / a.tiles : t) * kTileRows + static_cast<int64_t>(cta_rank) * 256 + quad * 32 + lane;
             const int64_t row1 = row0 + 128;
             const bool ok0 = row0 < a.n, ok1 = row1 < a.n;
             mbar_wait(&tfull_bar[sp], aph);
@@ -524,11 +489,31 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 float v0[32], v1[32];
                 tmem_ld_x32(t_acc + cb * 32, v0);
                 tmem_ld_x32(t_acc + N + cb * 32, v1);
+                if (RADAR_KLS_DEFER == 2) flush_pending();  // the slot number asked for one chunk ago has arrived by now
                 tmem_wait_ld();
                 if (cb == nq32 - 1) {  // both accumulator stages are free again once their last columns are in registers
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&tempty_bar[sp]);
+                }
+                if (BOOT) {
+                    if (!__all_sync(0xffffffffu, ok0 && ok1)) {  // rows past the end of the corpus arrive as zeros from TMA
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            if (!ok0) v0[c] = -CUDART_INF_F;
+                            if (!ok1) v1[c] = -CUDART_INF_F;
+                        }
+                    }
+                    float mine = -CUDART_INF_F;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float m = redux_fmax(fmaxf(v0[c], v1[c]));
+                        if (lane == c) mine = m;
+                    }
+                    const int qi = cb * 32 + lane;
+                    if (qi < a.q && mine > -CUDART_INF_F)
+                        atomicMax(a.tilemax + static_cast<int64_t>(qi) * a.tiles + t, f2ord(__fsub_rn(mine * INV, h_s[qi])));
+                    continue;
                 }
                 bool g0 = false, g1 = false, g2 = false, g3 = false;  // independent predicate chains, sub-tile 0
                 bool h0 = false, h1 = false, h2 = false, h3 = false;  // sub-tile 1
@@ -545,7 +530,11 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                     h3 |= v1[4 * c4 + 3] >= th.w;
                 }
                 const bool hit0 = (g0 | g1 | g2 | g3) && ok0, hit1 = (h0 | h1 | h2 | h3) && ok1;
+#ifdef RADAR_KLS_NORARE
+                if (false) {
+#else
                 if (__any_sync(0xffffffffu, hit0 | hit1)) {
+#endif
                     if (__any_sync(0xffffffffu, hit0))
                         append_survivors(v0, cb, row0, ok0, ok0 ? (g0 ? 1u : 0u) | (g1 ? 2u : 0u) | (g2 ? 4u : 0u) | (g3 ? 8u : 0u) : 0u);
                     if (__any_sync(0xffffffffu, hit1))
@@ -553,10 +542,12 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 }
             }
         }
-        flush_pending();
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(epi_done, 1u);
+        if (!BOOT) {
+            flush_pending();
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(epi_done, 1u);
+        }
     }
     tc_fence_before();
     __syncthreads();

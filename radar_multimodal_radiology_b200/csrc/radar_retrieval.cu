@@ -264,17 +264,18 @@ static int make_plan(const radar_corpus_t* c, int64_t q, const radar_search_para
         pl->n_pad = n_pad;
         pl->pool_cap = kls::pool_cap_for(n_pad);
         pl->tiles = ceil_div64(c->n, kls::kTileRows);
-        pl->sample_tiles = kls::sample_tiles_for(n_pad, ceil_div64(c->n, kls::kBootRows));
+        pl->sample_tiles = kls::sample_tiles_for(n_pad, pl->tiles);
         pl->units = sms / 2 < 1 ? 1 : sms / 2;
         pl->tile_q = n_pad;
         pl->q_tiles = 1;
         pl->parts = 1;
         const int64_t qp = n_pad;
-        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * (5 * qp + 8), 256) + sizeof(uint64_t) * qp * pl->pool_cap;
-        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr | boot counter | ucount] then the pools
+        pl->ks_zero_bytes = align_up(sizeof(uint32_t) * (5 * qp + 8), 256) + sizeof(uint64_t) * qp * pl->pool_cap +
+                            sizeof(uint32_t) * qp * pl->sample_tiles;
+        pl->off_ks_zero = carve(pl->ks_zero_bytes);  // [gcnt | lock | processed | best_n | gthr | - | ucount], the pools, the sample maxima
         pl->off_ks_pool = pl->off_ks_zero + align_up(sizeof(uint32_t) * (5 * qp + 8), 256);
+        pl->off_ks_tilemax = pl->off_ks_pool + sizeof(uint64_t) * qp * pl->pool_cap;
         pl->off_ks_best = carve(sizeof(uint64_t) * qp * kCandCap);
-        pl->off_ks_tilemax = carve(sizeof(uint32_t) * qp * pl->sample_tiles);
         pl->off_qerr = carve(sizeof(float) * qp);
         pl->off_ucount = pl->off_ks_zero + sizeof(uint32_t) * (5 * qp + 4);
         pl->off_ulist = carve(sizeof(uint32_t) * qp);
@@ -676,15 +677,6 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
             klf::klf_pack_kernel<<<static_cast<unsigned>((qp * 32 + 255) / 256), 256, 0, st>>>(pa);
         }
         RADAR_CUDA_CHECK(cudaGetLastError());
-        kls::BootArgs ba{};
-        ba.logq16 = corpus->logq16; ba.p16 = queries->p16; ba.entropy = queries->entropy; ba.qerr = qerr;
-        ba.n = corpus->n; ba.boot_tiles = ceil_div64(corpus->n, kls::kBootRows); ba.q = static_cast<int>(q);
-        ba.sample_tiles = pl.sample_tiles; ba.kp = pl.kp; ba.tilemax = tilemax; ba.gthr = gthr;
-        kls::kl_boot_kernel<<<static_cast<unsigned>(pl.sample_tiles < 4 * di.sms ? pl.sample_tiles : 4 * di.sms),
-                              kls::kBootThreads, 0, st>>>(ba);
-        RADAR_CUDA_CHECK(cudaGetLastError());
-        kls::kl_boot_threshold_kernel<<<static_cast<unsigned>(q), 32, 0, st>>>(ba);
-        RADAR_CUDA_CHECK(cudaGetLastError());
         CUtensorMap map_kl, map_q;
         memset(&map_kl, 0, sizeof map_kl);
         memset(&map_q, 0, sizeof map_q);
@@ -701,15 +693,18 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         sa.pool_cap = pl.pool_cap; sa.qshift = qshift; sa.gthr = gthr; sa.gcnt = gcnt; sa.lock = lock;
         sa.processed = processed; sa.best_n = best_n; sa.best = best; sa.pool = pool;
         sa.reload = kls::kThrReload;  // measured: 4 beats 1, 2, 8, 16 on kl_latency (fresher thresholds vs reload cost)
-        auto stream_kernel = pl.kl_fmt == klf::kFmtBf16x3 ? kls::kl_stream_kernel<klf::kFmtBf16x3>
-                             : pl.kl_fmt == klf::kFmtF16x1 ? kls::kl_stream_kernel<klf::kFmtF16x1>
-                                                           : kls::kl_stream_kernel<klf::kFmtF16x2>;
+        sa.total_tiles = pl.tiles; sa.tilemax = tilemax;
+        auto stream_kernel = pl.kl_fmt == klf::kFmtBf16x3 ? kls::kl_stream_kernel<klf::kFmtBf16x3, false>
+                             : pl.kl_fmt == klf::kFmtF16x1 ? kls::kl_stream_kernel<klf::kFmtF16x1, false>
+                                                           : kls::kl_stream_kernel<klf::kFmtF16x2, false>;
+        auto boot_kernel = pl.kl_fmt == klf::kFmtBf16x3 ? kls::kl_stream_kernel<klf::kFmtBf16x3, true>
+                           : pl.kl_fmt == klf::kFmtF16x1 ? kls::kl_stream_kernel<klf::kFmtF16x1, true>
+                                                         : kls::kl_stream_kernel<klf::kFmtF16x2, true>;
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kls::kStreamSmemBytes)));
-        int64_t units = pl.units;
-        if (units > pl.tiles) units = pl.tiles;
+        RADAR_CUDA_CHECK(cudaFuncSetAttribute(boot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              static_cast<int>(kls::kStreamSmemBytes)));
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
         cfg.blockDim = dim3(kls::kStreamThreads);
         cfg.dynamicSmemBytes = kls::kStreamSmemBytes;
         cfg.stream = st;
@@ -720,6 +715,22 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        {
+            // boot: the same tcgen05 pipeline over a strided sample of super-tiles -> per-query maxima -> initial thresholds
+            kls::StreamArgs sb = sa;
+            sb.tiles = pl.sample_tiles;
+            int64_t bunits = pl.units;
+            if (bunits > sb.tiles) bunits = sb.tiles;
+            cfg.gridDim = dim3(static_cast<unsigned>(bunits * 2));
+            RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, boot_kernel, map_kl, map_q, sb));
+            kls::BootArgs ba{};
+            ba.tilemax = tilemax; ba.sample_tiles = pl.sample_tiles; ba.kp = pl.kp; ba.gthr = gthr;
+            kls::kl_boot_threshold_kernel<<<static_cast<unsigned>(q), kls::kBootThreads, 0, st>>>(ba);
+            RADAR_CUDA_CHECK(cudaGetLastError());
+        }
+        int64_t units = pl.units;
+        if (units > pl.tiles) units = pl.tiles;
+        cfg.gridDim = dim3(static_cast<unsigned>(units * 2));
         if (g_prof_start) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_start, st));
         RADAR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, stream_kernel, map_kl, map_q, sa));
         if (g_prof_stop) RADAR_CUDA_CHECK(cudaEventRecord(g_prof_stop, st));

@@ -442,7 +442,7 @@ def test_kl_stream_adversarial_order_falls_back_exactly(dev):
     order = np.argsort(x, kind="stable")  # ascending key = descending KL
     p["c_pr"] = p["c_pr"][order]
     p["c_emb"] = p["c_emb"][order]
-    # k' = 48 candidates: the boot threshold is the 48th largest tile maximum, so ~48 x 256 cases of the sorted corpus beat
+    # k' = 48 candidates: the boot threshold is the 48th largest super-tile maximum, so ~48 x 512 cases of the sorted corpus beat
     # it -- more than the 8192-entry pool of a query holds
     idx = _index(p, dev, precision="bf16", overfetch=48)
     s, i = _search(idx, p, "kl", 10)
