@@ -74,9 +74,12 @@ __host__ __device__ inline int pool_cap_for(int n_pad) {  // entries of one quer
     int c = (1 << 20) / n_pad;
     return c > 8192 ? 8192 : (c < 2048 ? 2048 : c);
 }
-inline int sample_tiles_for(int n_pad, int64_t tiles) {  // sampled super-tiles of the boot pass
+inline int sample_tiles_for(int n_pad, int64_t tiles) {  // sampled super-tiles of the boot pass: ~10 % of the shard
     (void)n_pad;
-    return static_cast<int>(kMaxSample < tiles ? kMaxSample : tiles);
+    int64_t s = tiles / 10;
+    if (s < 256) s = 256;
+    if (s > kMaxSample) s = kMaxSample;
+    return static_cast<int>(s < tiles ? s : tiles);
 }
 
 // ---- boot threshold: k'-th largest sampled super-tile maximum per query -------------------------------------------

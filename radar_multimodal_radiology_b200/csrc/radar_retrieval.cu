@@ -824,6 +824,7 @@ int radar_search(const radar_corpus_t* corpus, const radar_queries_t* queries, c
         r.q_emb = queries->emb_f32; r.p16 = queries->p16; r.entropy = queries->entropy;
         r.c_emb = corpus->emb_f32; r.logq16 = corpus->logq16; r.qmap = nullptr; r.nq = q; r.d = corpus->d;
         r.mode = params->mode; r.alpha = alpha; r.oma = oma; r.R = pl.R; r.sel = sel; r.done = done;
+        r.qerr = qerr; r.bound = bound; r.k = params->k;
         RADAR_CUDA_CHECK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               static_cast<int>(kRescoreSmemBytes)));
         rescore_kernel<<<static_cast<unsigned>(ceil_div64(q, kRsWarps)), kRsWarps * 32, kRescoreSmemBytes, st>>>(r);

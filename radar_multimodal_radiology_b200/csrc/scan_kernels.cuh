@@ -354,6 +354,13 @@ struct RescoreArgs {
     int R;
     uint64_t* sel;
     const uint8_t* done;  // nullable: queries already finished by kl_finish_kernel
+    // pruning (all nullable / 0): sel rows arrive sorted by FILTER key.  With f_k the k-th best filter key, a candidate with
+    // f < f_k - 2 qerr cannot reach the canonical top-k (k candidates have canonical >= f_k - qerr, its own is < f_k - qerr),
+    // so its 2 KB embedding row is never fetched: the entry is emptied and its filter key joins the bound of dropped
+    // candidates, where the certificate of final_kernel sees it like any other dropped case.
+    const float* qerr;
+    float* bound;
+    int k;
 };
 
 // One warp per query, lanes = candidates.  The embedding rows of the (up to) 32 candidates of a group are fetched
@@ -376,10 +383,20 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(const RescoreArg
     const int64_t qid = a.qmap ? a.qmap[qi] : qi;
     const bool has_ip = a.mode != RADAR_MODE_KL, has_kl = a.mode != RADAR_MODE_DPR;
     const float h = has_kl ? a.entropy[qid] : 0.0f;
+    float prune_below = -CUDART_INF_F, pruned_max = -CUDART_INF_F;
+    if (a.qerr && a.k >= 1 && a.k <= a.R) {
+        const uint64_t ck = a.sel[qi * a.R + a.k - 1];
+        if (ck != 0ull) prune_below = composite_key(ck) - 2.0f * a.qerr[qid];
+    }
     for (int g0 = 0; g0 < a.R; g0 += 32) {
         const int ci = g0 + lane;
         const uint64_t c = ci < a.R ? a.sel[qi * a.R + ci] : 0ull;
-        const bool live = c != 0ull;
+        bool live = c != 0ull;
+        if (live && composite_key(c) < prune_below) {
+            pruned_max = fmaxf(pruned_max, composite_key(c));
+            a.sel[qi * a.R + ci] = 0ull;
+            live = false;
+        }
         const uint32_t row = live ? composite_row(c) : 0u;
         const unsigned live_mask = __ballot_sync(0xffffffffu, live);
         if (live_mask == 0u) continue;
@@ -424,6 +441,11 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(const RescoreArg
             }
             a.sel[qi * a.R + ci] = make_composite(canonical_key(a.mode, ip, x, h, a.alpha, a.oma), row);
         }
+    }
+    if (a.bound) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pruned_max = fmaxf(pruned_max, __shfl_xor_sync(0xffffffffu, pruned_max, o));
+        if (lane == 0 && pruned_max > -CUDART_INF_F) a.bound[qi] = fmaxf(a.bound[qi], pruned_max);
     }
 }
 
