@@ -234,6 +234,15 @@ __device__ __noinline__ void refresh_threshold(const StreamArgs& a, int qi, uint
 
 // FMT (klf::kFmt*): bf16 hi/lo x 3 products on klpack (64 B rows), or fp16 x 1 / x 2 products on kl16 (32 B rows: half
 // the HBM bytes per case); the fp16 accumulators are scaled by 2^24 (kl_filter.cuh), thresholds are compared in scaled units
+#ifdef RADAR_KLS_TIMING
+// experiment aid (tools/kls_timing.py): per CTA [start, after prologue, end, rare-path visits] of the last stream launch
+__device__ unsigned long long g_kls_timing[296 * 4];
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
 // BOOT: the same pipeline over a strided SAMPLE of super-tiles; the epilogue only reduces, per query, the maximum filter key of
 // every sampled super-tile (redux.sync.max.f32 over the 32 cases of a warp, one atomicMax per query and warp) -> tilemax.
 template <int FMT, bool BOOT>
@@ -270,6 +279,9 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     const int spairs = kTmemCols / (2 * N);  // accumulator stage pairs (1 .. 8)
     const uint32_t idesc = FMT == kFmtBf16x3 ? make_idesc_mn(kSubRows, N) : klf::make_idesc_f16_mn(kSubRows, N);
 
+#ifdef RADAR_KLS_TIMING
+    if (!BOOT && threadIdx.x == 0) { g_kls_timing[blockIdx.x * 4 + 0] = gtimer(); g_kls_timing[blockIdx.x * 4 + 3] = 0ull; }
+#endif
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_kl);
         prefetch_tmap(&map_q);
@@ -293,6 +305,9 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+#ifdef RADAR_KLS_TIMING
+    if (!BOOT && threadIdx.x == 0) g_kls_timing[blockIdx.x * 4 + 1] = gtimer();
+#endif
     if (tmem_base != 0) {
         if (threadIdx.x == 0) printf("radar kl_stream: unexpected TMEM base %u\n", tmem_base);
         __trap();
@@ -538,6 +553,9 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
 #else
                 if (__any_sync(0xffffffffu, hit0 | hit1)) {
 #endif
+#ifdef RADAR_KLS_TIMING
+                    if (lane == 0) atomicAdd(&g_kls_timing[blockIdx.x * 4 + 3], 1ull);
+#endif
                     if (__any_sync(0xffffffffu, hit0))
                         append_survivors(v0, cb, row0, ok0, ok0 ? (g0 ? 1u : 0u) | (g1 ? 2u : 0u) | (g2 ? 4u : 0u) | (g3 ? 8u : 0u) : 0u);
                     if (__any_sync(0xffffffffu, hit1))
@@ -554,6 +572,9 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+#ifdef RADAR_KLS_TIMING
+    if (!BOOT && threadIdx.x == 0) g_kls_timing[blockIdx.x * 4 + 2] = gtimer();
+#endif
     cluster_sync_all();
     if (warp == 1) tmem_dealloc_pair(tmem_base);
 }

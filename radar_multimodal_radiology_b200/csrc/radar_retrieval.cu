@@ -995,3 +995,9 @@ int radar_project_normalize_tc(const float* x, const float* w, const float* bias
 }
 
 }  // extern "C"
+
+#ifdef RADAR_KLS_TIMING
+extern "C" int radar_debug_kls_timing(unsigned long long* out) {  // experiment builds only (tools/kls_timing.py)
+    return cudaMemcpyFromSymbol(out, radar::kls::g_kls_timing, sizeof(unsigned long long) * 296 * 4) == cudaSuccess ? 0 : 1;
+}
+#endif
