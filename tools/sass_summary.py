@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-WATCH = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "STTM", "UTCATOMSWS", "SYNCS", "FMNMX3", "FMNMX", "FFMA", "HMMA", "VOTE",
+WATCH = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "STTM", "UTCATOMSWS", "SYNCS", "CREDUX", "FMNMX3", "FMNMX", "FFMA", "HMMA", "VOTE",
          "ATOM", "RED", "LDG", "STG", "LDS", "STS", "BAR", "ELECT"]
 
 
