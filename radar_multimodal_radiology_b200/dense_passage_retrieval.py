@@ -26,6 +26,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ._nvtx import annotate as _nvtx_annotate
 from .config import RetrievalConfig
 from .index import RadarIndex, project_normalize
 from .knowledge import OBSERVATION_NAMES, observation_bits  # noqa: F401 (re-exported)
@@ -113,6 +114,7 @@ class HybridRetriever(nn.Module):
         self.encode_batch = encode_batch
         self.case_bits: Optional[torch.Tensor] = None  # uint16[N] observation sets, CheXpert-14 bit order
 
+    @_nvtx_annotate("retriever.build_indices")
     def build_indices(self, passages: List[str], observations: List[List[str]],
                       observation_probs=None, embeddings=None) -> None:
         """Encode and index ``passages`` (dpr.py:278-303).
@@ -144,6 +146,7 @@ class HybridRetriever(nn.Module):
         self.semantic_index = index
         logger.info("GPU index built: %d passages", index.ntotal)
 
+    @_nvtx_annotate("retriever.retrieve")
     def retrieve(self, query_embed: torch.Tensor, k: int = None, query_probs=None, mask=None
                  ) -> Tuple[List[str], List[float]]:
         """Best-first (passages, scores) for ONE query embedding (dpr.py:305-318)."""

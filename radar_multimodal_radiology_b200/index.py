@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from ._nvtx import annotate as _nvtx_annotate, range_ as _nvtx_range
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
@@ -207,6 +208,7 @@ class RadarIndex:
             return int(self.logq16.shape[0])
         return 0
 
+    @_nvtx_annotate("index.add")
     def add(self, x: ArrayLike) -> None:
         """Append embedding rows (float32[N,d]); ``faiss.IndexFlatIP.add`` (dpr.py:298).  Like faiss, the rows are
         COPIED into the index (the caller may reuse its buffer)."""
@@ -228,6 +230,7 @@ class RadarIndex:
         self.emb_max_norm = max(self.emb_max_norm, float(mx.item()))
         self.generation += 1
 
+    @_nvtx_annotate("index.add_observations")
     def add_observations(self, probs: ArrayLike) -> None:
         """Append observation-probability rows (float32[N,14], CheXpert-14 order) -- K1 corpus side."""
         p = _as_device_f32(probs, self.device)
@@ -255,6 +258,7 @@ class RadarIndex:
         self.generation += 1
 
     # ---- persistence (the reference rebuilds its index in RAM on every run) ----------
+    @_nvtx_annotate("index.save")
     def save(self, path: str) -> None:
         """Write this (shard of the) index as ``<path>.safetensors`` + ``<path>.json``.
 
@@ -362,6 +366,7 @@ class RadarIndex:
             raise ValueError(f"mode must be one of {sorted(L.MODE_BY_NAME)}")
         return L.MODE_BY_NAME[mode]
 
+    @_nvtx_annotate("index.search")
     def search(self, x: Optional[ArrayLike], k: int, query_probs: Optional[ArrayLike] = None,
                mask: Optional[ArrayLike] = None, alpha: float = 0.5, mode: Optional[str] = None,
                precision: Optional[str] = None, algo: Optional[str] = None, collect_stats: bool = False,

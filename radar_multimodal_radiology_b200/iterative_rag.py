@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
+from ._nvtx import annotate as _nvtx_annotate
 from .config import IterativeRAGConfig
 
 logger = logging.getLogger(__name__)
@@ -232,6 +233,7 @@ def gather_case_bits(table: torch.Tensor, ids: torch.Tensor, idx_offset: int = 0
     return out
 
 
+@_nvtx_annotate("rag.batched_retrieval_round")
 def batched_retrieval_round(index, query_embeds: Optional[torch.Tensor], query_probs: torch.Tensor,
                             missing_bits: torch.Tensor, case_bits_table: Optional[torch.Tensor], k: int,
                             alpha: float = 0.5, mode: Optional[str] = None, search_fn: Optional[Callable] = None

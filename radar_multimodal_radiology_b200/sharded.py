@@ -17,6 +17,8 @@ from typing import Callable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ._nvtx import annotate as _nvtx_annotate, range_ as _nvtx_range
+
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     per = -(-n // world)
@@ -88,6 +90,7 @@ class ShardedRadarIndex:
 
     # ---- queries that arrive on the host: every rank uploads 1/G of the rows over its own PCIe link and the ranks
     # exchange the slices over NVLink, instead of G copies of the whole batch crossing PCIe
+    @_nvtx_annotate("sharded.upload_queries")
     def upload_queries(self, host: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``host``: the same (pinned) [Q, ...] tensor on every rank.  Returns the [Q, ...] device tensor."""
         if self.world == 1:
@@ -108,6 +111,7 @@ class ShardedRadarIndex:
         out.copy_(padded[:q])
         return out
 
+    @_nvtx_annotate("sharded.search")
     def search(self, x, k: int, query_probs=None, mask=None, alpha: float = 0.5, mode: Optional[str] = None,
                **kw) -> Tuple[torch.Tensor, torch.Tensor]:
         if k > self.n_total:
@@ -128,9 +132,11 @@ class ShardedRadarIndex:
                                          return_packed=True, **kw)[2]
         # concatenated-along-dim-0 output is the form both NCCL and gloo accept; viewed as [G, Q, k]
         gathered = torch.empty((self.world * nq, k), dtype=torch.int64, device=self.device)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        with _nvtx_range("sharded.all_gather"):
+            dist.all_gather_into_tensor(gathered, packed, group=self.group)
         gathered = gathered.view(self.world, nq, k)
-        if self._merge is not None:
-            return self._merge(gathered, k, mname)
-        from .index import merge_packed
-        return merge_packed(gathered, k, mname)
+        with _nvtx_range("sharded.merge"):
+            if self._merge is not None:
+                return self._merge(gathered, k, mname)
+            from .index import merge_packed
+            return merge_packed(gathered, k, mname)

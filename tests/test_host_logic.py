@@ -264,3 +264,24 @@ def test_batched_retrieval_metrics_match_reference_fixtures(ref_fixtures):
                 assert abs(float(values[i]) - c[name]) < 1e-12, (name, i, float(values[i]), c[name])
                 checked += 1
     assert checked >= 10 * len(cases)
+
+
+def test_nvtx_ranges_are_harmless_without_a_profiler(monkeypatch):
+    """NVTX ranges around build / search / exchange.  They must never change a result or raise."""
+    from radar_multimodal_radiology_b200 import _nvtx
+    calls = []
+
+    @_nvtx.annotate("unit")
+    def f(x, y=1):
+        calls.append((x, y))
+        return x + y
+
+    assert f(2, y=3) == 5 and calls == [(2, 3)] and f.__name__ == "f"
+    with _nvtx.range_("outer"):
+        with _nvtx.range_("inner"):
+            pass
+    with pytest.raises(ZeroDivisionError):  # the range is closed on the way out of an exception
+        with _nvtx.range_("raises"):
+            1 / 0
+    monkeypatch.setattr(_nvtx, "_ENABLED", False)
+    assert f(1) == 2
