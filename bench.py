@@ -17,6 +17,8 @@ other BASELINE configuration as `secondary[...]` records (a few steps each):
     hybrid_10m_k32         configs[3] as written: top-k = 32
     rag_rounds             configs[4]: 3 masked re-retrieval rounds x 16 384 queries, top-k = 5
     kl_latency             KL-only, 10M cases, 32 queries, top-k = 32 (the HBM-bound regime, BASELINE.md row 4')
+    dpr_latency            DPR, 10M cases, ONE query per call, top-k = 10: the reference's own call pattern
+                           (IndexFlatIP.search with nq = 1, dpr.py:312-314) -- HBM-bound: 1 024 B of bf16 embedding per case
     dpr_377k / kl_377k     configs[2] / configs[1]: 377k cases, 65 536 queries, top-k = 10
     clustered_2m / adversarial_2m   structured corpora (clustered embeddings; rows sorted so that every query's
                            scores keep rising along the sweep) -- the threshold filter's rare path under timing
@@ -49,12 +51,13 @@ WORKLOADS = {
     "kl_377k": dict(mode="kl", n=377_000, q=65536, k=10),
     "dpr_377k": dict(mode="dpr", n=377_000, q=65536, k=10),
     "kl_latency": dict(mode="kl", n=10_000_000, q=32, k=32),
+    "dpr_latency": dict(mode="dpr", n=10_000_000, q=1, k=10),
     "rag_rounds": dict(mode="hybrid", n=10_000_000, q=16384, k=5, masked=True, rounds=3),
     "clustered_2m": dict(mode="hybrid", n=2_000_000, q=16384, k=10, corpus="clustered"),
     "adversarial_2m": dict(mode="hybrid", n=2_000_000, q=16384, k=10, corpus="adversarial"),
     "smoke": dict(mode="hybrid", n=200_000, q=1024, k=10),
 }
-SECONDARY = ["hybrid_10m_bf16", "hybrid_10m_k32", "rag_rounds", "kl_latency", "dpr_377k", "kl_377k",
+SECONDARY = ["hybrid_10m_bf16", "hybrid_10m_k32", "rag_rounds", "kl_latency", "dpr_latency", "dpr_377k", "kl_377k",
              "clustered_2m", "adversarial_2m"]
 D = 512
 ALPHA = 0.5

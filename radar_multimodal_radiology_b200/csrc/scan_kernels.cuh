@@ -303,25 +303,61 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* 
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
     }
-    // the slabs' buffers stream through a kCandCap-entry working set; whenever it fills up the register radix
-    // select keeps the best R (everything it drops has key <= the returned R-th key)
+    // The largest final threshold b is a lower bound of the k'-th best key of the whole corpus, and every case with a key >= b
+    // still sits in some slab's buffer (a case is only ever dropped below a threshold <= b).  So entries below b -- most of what
+    // the buffers hold: each keeps up to 192 admitted under older, looser thresholds -- are skipped on the way in, and the
+    // register radix select below (issue-bound: ~600 instructions per call) runs once instead of once per 200 entries read.
+    // Every compaction returns the R-th best key so far: a running threshold, so that the stream of entries thins out as it is
+    // read (a short sweep never tightens the prepass threshold inside the filter: ~2 900 entries per query reach this kernel and
+    // cost 14 compactions without the running threshold, 2 - 3 with it).
+    uint32_t keep_from = (thr_final && b > -CUDART_INF_F) ? f2ord(b) : 0u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
     int fill = 0;
+    auto append = [&](uint64_t c, bool valid) {  // warp-wide: compacting append of the lanes' entries that can still matter
+        const bool keep = valid && c != 0ull && static_cast<uint32_t>(c >> 32) >= keep_from;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        const int n = __popc(m);
+        if (n == 0) return;
+        if (fill + n > kCandCap) {
+            __syncwarp();
+            const float t = warp_compact(w, fill, R, lane);  // everything it dropped is <= t; ties with t stay admissible
+            b = fmaxf(b, t);
+            keep_from = max(keep_from, f2ord(t));
+            fill = R;
+        }
+        if (keep) w[fill + __popc(m & lt_mask)] = c;  // (entries of this chunk that fell below the new threshold are sorted out later)
+        fill += n;
+    };
     uint32_t cnt_l = 0;  // counts of 32 slabs at a time, one per lane: the per-slab loop below never waits for a count
-    for (int p = 0; p < parts; ++p) {
-        if ((p & 31) == 0) cnt_l = p + lane < parts ? cnt[qi * parts + p + lane] : 0u;
-        const int c = static_cast<int>(__shfl_sync(0xffffffffu, cnt_l, p & 31));
-        const uint64_t* src = cand + (qi * parts + p) * cap;
-        int done = 0;
-        while (done < c) {
-            const int take = min(c - done, kCandCap - fill);
-            for (int i = lane; i < take; i += 32) w[fill + i] = src[done + i];
-            fill += take;
-            done += take;
-            if (fill == kCandCap) {
-                __syncwarp();
-                b = fmaxf(b, warp_compact(w, fill, R, lane));
-                fill = R;
-            }
+    // Slabs are taken eight at a time: the first 32 entries of each are requested back to back and only then appended, so a
+    // query with many slabs (a single-query search sweeps 74 x 2 of them) pays one load round trip per eight slabs.
+    constexpr int kBatch = 8;
+    for (int p0 = 0; p0 < parts; p0 += kBatch) {
+        int c[kBatch];
+        uint64_t first[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int p = p0 + u;
+            if ((p & 31) == 0) cnt_l = p + lane < parts ? cnt[qi * parts + p + lane] : 0u;  // kBatch divides 32
+            c[u] = p < parts ? static_cast<int>(__shfl_sync(0xffffffffu, cnt_l, p & 31)) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u)
+            first[u] = lane < c[u] ? cand[(qi * parts + p0 + u) * cap + lane] : 0ull;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (c[u] == 0) continue;
+            append(first[u], lane < c[u]);
+            if (c[u] <= 32) continue;
+            const uint64_t* src = cand + (qi * parts + p0 + u) * cap;
+            uint64_t more[kCandCap / 32 - 1];  // the rest of the buffer: all loads in flight before the first append
+#pragma unroll
+            for (int j = 1; j < kCandCap / 32; ++j) more[j - 1] = 32 * j + lane < c[u] ? src[32 * j + lane] : 0ull;
+#pragma unroll
+            for (int j = 1; j < kCandCap / 32; ++j)
+                if (32 * j < c[u]) append(more[j - 1], 32 * j + lane < c[u]);
+            for (int i0 = kCandCap; i0 < c[u]; i0 += 32)  // (a caller with larger buffers than kCandCap)
+                append(i0 + lane < c[u] ? src[i0 + lane] : 0ull, i0 + lane < c[u]);
         }
     }
     __syncwarp();
