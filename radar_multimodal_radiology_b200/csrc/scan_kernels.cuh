@@ -329,12 +329,13 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* 
         fill += n;
     };
     uint32_t cnt_l = 0;  // counts of 32 slabs at a time, one per lane: the per-slab loop below never waits for a count
-    // Slabs are taken eight at a time: the first 32 entries of each are requested back to back and only then appended, so a
-    // query with many slabs (a single-query search sweeps 74 x 2 of them) pays one load round trip per eight slabs.
-    constexpr int kBatch = 8;
+    // Slabs are taken four at a time and a slab's whole buffer (up to kCandCap entries = 8 loads per lane) is requested before the
+    // first entry is appended: 32 loads in flight per lane, so a query with many slabs (a single-query search sweeps 74 x 2 of
+    // them) pays one load round trip per four slabs instead of several per slab.
+    constexpr int kBatch = 4, kChunks = kCandCap / 32;
     for (int p0 = 0; p0 < parts; p0 += kBatch) {
         int c[kBatch];
-        uint64_t first[kBatch];
+        uint64_t v[kBatch][kChunks];
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             const int p = p0 + u;
@@ -342,20 +343,17 @@ __global__ void __launch_bounds__(kSelWarps * 32) select_kernel(const uint64_t* 
             c[u] = p < parts ? static_cast<int>(__shfl_sync(0xffffffffu, cnt_l, p & 31)) : 0;
         }
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-            first[u] = lane < c[u] ? cand[(qi * parts + p0 + u) * cap + lane] : 0ull;
+        for (int u = 0; u < kBatch; ++u) {
+            const uint64_t* src = cand + (qi * parts + p0 + u) * cap;
+#pragma unroll
+            for (int j = 0; j < kChunks; ++j) v[u][j] = 32 * j + lane < c[u] ? src[32 * j + lane] : 0ull;
+        }
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-            if (c[u] == 0) continue;
-            append(first[u], lane < c[u]);
-            if (c[u] <= 32) continue;
+#pragma unroll
+            for (int j = 0; j < kChunks; ++j)
+                if (32 * j < c[u]) append(v[u][j], 32 * j + lane < c[u]);
             const uint64_t* src = cand + (qi * parts + p0 + u) * cap;
-            uint64_t more[kCandCap / 32 - 1];  // the rest of the buffer: all loads in flight before the first append
-#pragma unroll
-            for (int j = 1; j < kCandCap / 32; ++j) more[j - 1] = 32 * j + lane < c[u] ? src[32 * j + lane] : 0ull;
-#pragma unroll
-            for (int j = 1; j < kCandCap / 32; ++j)
-                if (32 * j < c[u]) append(more[j - 1], 32 * j + lane < c[u]);
             for (int i0 = kCandCap; i0 < c[u]; i0 += 32)  // (a caller with larger buffers than kCandCap)
                 append(i0 + lane < c[u] ? src[i0 + lane] : 0ull, i0 + lane < c[u]);
         }
