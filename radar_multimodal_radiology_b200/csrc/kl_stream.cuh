@@ -82,6 +82,13 @@ inline int sample_tiles_for(int n_pad, int64_t tiles) {  // sampled super-tiles 
     return static_cast<int>(s < tiles ? s : tiles);
 }
 
+// Programmatic dependent launch (the KL stream chain is latency-bound: six short kernels around a 0.12 ms sweep).  A kernel
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor still runs; it must call
+// pdl_wait() before it touches anything the predecessor writes (a no-op when launched without the attribute).  pdl_trigger()
+// lets the NEXT kernel in the stream be scheduled from now on.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- boot threshold: k'-th largest sampled super-tile maximum per query -------------------------------------------
 // The maxima come from the BOOT instantiation of the stream kernel (filter keys of a strided sample of super-tiles): the
 // k'-th largest is a valid lower bound of the k'-th best filter key of the whole corpus (tile maxima are distinct cases).
@@ -96,6 +103,8 @@ __global__ void __launch_bounds__(kBootThreads) kl_boot_threshold_kernel(const B
     static_assert(kMaxSample % kBootThreads == 0, "sample tiles per thread");
     __shared__ int cnt[2][3][kBootThreads / 32];
     const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();  // the stream kernel may set up its barriers / tensor memory while the thresholds are selected
+    pdl_wait();     // the boot sweep's maxima
     const uint32_t* src = a.tilemax + static_cast<int64_t>(qi) * a.sample_tiles;
     uint32_t val[kMaxSample / kBootThreads];
 #pragma unroll
@@ -298,13 +307,15 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
         for (int i = 0; i < kMaxN / 32; ++i) refresh_req[i] = 0u;
         *epi_done = 0u;
     }
+    pdl_trigger();  // BOOT: the threshold kernel's CTAs may be scheduled; stream: the final kernel's (they wait for this grid)
     if (warp == 1) tmem_alloc_pair(tmem_slot);
-    for (int i = threadIdx.x; i < N; i += kStreamThreads) h_s[i] = a.qshift[i];
+    for (int i = threadIdx.x; i < N; i += kStreamThreads) h_s[i] = a.qshift[i];  // written by the pack kernel: long complete
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (!BOOT) pdl_wait();  // everything above overlapped the threshold kernel; the thresholds are read below
 #ifdef RADAR_KLS_TIMING
     if (!BOOT && threadIdx.x == 0) g_kls_timing[blockIdx.x * 4 + 1] = gtimer();
 #endif
@@ -605,6 +616,7 @@ __global__ void __launch_bounds__(kFinThreads) kl_stream_final_kernel(const Stre
     __shared__ uint64_t surv[kFinCap];
     __shared__ int surv_n;
     const int qi = blockIdx.x, tid = threadIdx.x;
+    pdl_wait();  // the stream kernel's pools, counts and final thresholds
     if (tid < kObsPad) ps[tid] = a.p16[qi * kObsPad + tid];
     if (tid == 0) surv_n = 0;
     __syncthreads();
