@@ -1034,3 +1034,9 @@ extern "C" int radar_debug_kls_timing(unsigned long long* out) {  // experiment 
     return cudaMemcpyFromSymbol(out, radar::kls::g_kls_timing, sizeof(unsigned long long) * 296 * 4) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+#ifdef RADAR_TC_TIMING
+extern "C" int radar_debug_tc_timing(unsigned long long* out) {  // experiment builds only (tools/tc_timing.py)
+    return cudaMemcpyFromSymbol(out, radar::tc::g_tc_timing, sizeof(unsigned long long) * 296 * 2) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -401,6 +401,9 @@ __device__ __forceinline__ void st_progress(unsigned long long* p, unsigned long
 
 // KB_T > 0: the embedding K-block count (d / 64) is a compile-time constant and the issue / load loops unroll
 // completely (KB_T = 8 is BiomedCLIP's d = 512); KB_T = 0: d is read from the arguments.
+#ifdef RADAR_TC_TIMING
+__device__ unsigned long long g_tc_timing[296 * 2];  // experiment aid (tools/tc_timing.py): per CTA [start, end] of the last real pass
+#endif
 template <int MODE, int KB_T>
 __global__ void __launch_bounds__(threads_for_mode(MODE), 1)
 tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_constant__ CUtensorMap map_kl,
@@ -450,6 +453,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     const int64_t items = a.q_tiles * a.parts;
     const int64_t tile_step = static_cast<int64_t>(BLOCK_N) * a.tile_stride;  // the prepass samples every tile_stride-th tile
 
+#ifdef RADAR_TC_TIMING
+    if (!a.prepass && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tc_timing[blockIdx.x * 2]));
+#endif
     unsigned long long clk0 = 0, ns0 = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         clk0 = clock64();
@@ -971,6 +977,9 @@ tc_filter_kernel(const __grid_constant__ CUtensorMap map_emb, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+#ifdef RADAR_TC_TIMING
+    if (!a.prepass && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_tc_timing[blockIdx.x * 2 + 1]));
+#endif
     cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still touch it
     if (warp == 1) tmem_dealloc_pair(tmem_base);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
