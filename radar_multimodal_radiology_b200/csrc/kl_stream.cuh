@@ -50,7 +50,8 @@ constexpr int kMaxN = 256;              // queries per launch (MMA N)
 #endif
 // park a pooled append until the thread's next visit of the rare path instead of waiting ~700 cycles for its slot number.
 // Measured: SLOWER (0.125 -> 0.151 ms on kl_latency) -- entries reach the pool late, refreshes see fewer of them, thresholds
-// tighten later and more cases survive.  Kept as a build option.
+// tighten later and more cases survive; flushing at the next chunk instead (one tile later) measured no different from not
+// deferring at all.  Kept as a build option.
 constexpr bool kDeferAppends = RADAR_KLS_DEFER != 0;
 constexpr int kIssuers = RADAR_KLS_ISSUERS;  // MMA issuer warps (warp 1 and warp 11) taking alternate super-tiles
 constexpr int kStreamThreads = 384;     // warp 0 TMA, warps 1 / 11 MMA, warps 2-5 / 6-9 epilogue sets (alternating super-tiles),
@@ -518,7 +519,6 @@ kl_stream_kernel(const __grid_constant__ CUtensorMap map_kl, const __grid_consta
                 float v0[32], v1[32];
                 tmem_ld_x32(t_acc + cb * 32, v0);
                 tmem_ld_x32(t_acc + N + cb * 32, v1);
-                if (RADAR_KLS_DEFER == 2) flush_pending();  // the slot number asked for one chunk ago has arrived by now
                 tmem_wait_ld();
                 if (cb == nq32 - 1) {  // both accumulator stages are free again once their last columns are in registers
                     tc_fence_before();
