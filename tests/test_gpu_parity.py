@@ -308,6 +308,20 @@ def test_tc_filter_sampled_prepass_on_short_sweeps(dev, mode, k):
     assert np.mean([len(set(a) & set(b)) / k for a, b in zip(i, wi)]) >= 0.999
 
 
+@pytest.mark.parametrize("mode,q,k", [("dpr", 1, 10), ("hybrid", 3, 32), ("dpr", 1, 100)])
+def test_few_queries_over_many_slabs_select_stays_exact(dev, mode, q, k):
+    """One query per call (the reference's nq = 1 pattern, dpr.py:312-314): the single query tile is cut into one slab per CTA
+    pair, so select_kernel merges ~70 x 2 candidate buffers for one query -- the streaming top-R with a running threshold, buffers
+    requested four at a time -- and the result must stay the canonical one."""
+    p = make_problem(600011, q, d=64, seed=123 + k)
+    ws, wi = _oracle(p, mode, k)
+    idx = _index(p, dev, precision="fp32", algo="tc")
+    s, i = _search(idx, p, mode, k)
+    st = idx.last_stats
+    assert st.algo_used == 2 and st.parts >= 32, st
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+
+
 def test_tc_filter_prepass_with_many_candidates(dev):
     """top-32 (k' = 96 candidates per query) over a 1.3 M-row shard: the sampled prepass runs with ~4 k' groups and the
     fp32 result stays bit-identical to the oracle."""
